@@ -1,0 +1,1161 @@
+// occl_b200.cu -- hand-written sm_100a kernels + the C-ABI of include/occl_b200.h.
+//
+// Hot path of MILAB-IIT-CV/OcclusionEnv (environment.py:352-396 step, :302-328 reset render) for N
+// environments at once.  Four kernels per transition, all on the caller's stream:
+//
+//   pose_kernel      one thread per env: action -> (el, az) -> camera centre -> look-at R, T, with
+//                    forward-mode tangents d/d_el, d/d_az carried as dual numbers       (north-star 1)
+//   project_kernel   one thread per (env, vertex): world -> view -> NDC, z := view z    (north-star 1)
+//   raster_kernel    one CTA per (env, image tile): faces are set up, culled and compacted into a
+//                    shared-memory list with warp ballots (2); a warp per face scatters soft-
+//                    silhouette factors and the nearest-z key into per-pixel accumulators in shared
+//                    memory (3,4); the epilogue blends, shades, writes RGBD / occlusion map with
+//                    coalesced stores and reduces loss, gradient and pixel counts with warp shuffles (5,6)
+//   finalize_kernel  one thread per env: tile partials -> loss, reward, done, state, d reward/d action
+//
+// Bit-exactness: every expression that decides a hit, its sign, the nearest face or the K-nearest
+// set is evaluated in the operation order of pytorch3d's rasteriser with
+// IEEE fp32 add/mul/div/sqrt and NO fused multiply-add: this translation unit is compiled with
+// -fmad=false (see occlusionenv_b200/build.py).  Nothing here falls back to a CPU path.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "occl_b200.h"
+
+#define OCCL_THREADS 256
+#define OCCL_WARPS (OCCL_THREADS / 32)
+#define LIST_CAP 384          // face records staged in shared memory per round
+#define SCAN_CHUNK OCCL_THREADS
+#define BIG_FACE_PX 192       // faces covering more tile pixels than this are rasterised by the whole CTA
+#define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
+#define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
+#define REC_WORDS 16
+
+static thread_local char g_last_err[256] = "";
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+struct Partial {
+  double loss;     // sum occl^2 over the tile
+  double objsq;    // sum (sum_i A_i)^2
+  double gl[2];    // d loss / d el, d loss / d az
+  int ncov[OCCL_MAX_OBJ];
+  int nvis[OCCL_MAX_OBJ];
+};
+
+__device__ __forceinline__ float pix_to_ndc(int i, int S) {
+  // PixToNonSquareNdc for a square image: -1 + (2 i + 1) / S           
+  return -1.0f + (2.0f * (float)i + 1.0f) / (float)S;
+}
+
+// Dual number: value + tangents w.r.t. (elevation, azimuth). The value part uses exactly the
+// operations of the oracle / reference so that the pose is bit-identical.
+struct Dual {
+  float v, d0, d1;
+};
+__device__ __forceinline__ Dual mk(float v) { return Dual{v, 0.f, 0.f}; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return Dual{a.v + b.v, a.d0 + b.d0, a.d1 + b.d1}; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return Dual{a.v - b.v, a.d0 - b.d0, a.d1 - b.d1}; }
+__device__ __forceinline__ Dual operator-(Dual a) { return Dual{-a.v, -a.d0, -a.d1}; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) {
+  return Dual{a.v * b.v, a.d0 * b.v + a.v * b.d0, a.d1 * b.v + a.v * b.d1};
+}
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  const float q = a.v / b.v;
+  return Dual{q, (a.d0 - q * b.d0) / b.v, (a.d1 - q * b.d1) / b.v};
+}
+__device__ __forceinline__ Dual dsqrt(Dual a) {
+  const float s = sqrtf(a.v);
+  const float h = s > 0.f ? 0.5f / s : 0.f;
+  return Dual{s, a.d0 * h, a.d1 * h};
+}
+__device__ __forceinline__ void dnormalize(const Dual v[3], float eps, Dual o[3]) {
+  // torch.nn.functional.normalize: v / max(||v||, eps)
+  Dual n = dsqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+  Dual d = n.v > eps ? n : mk(eps);
+  o[0] = v[0] / d;
+  o[1] = v[1] / d;
+  o[2] = v[2] / d;
+}
+__device__ __forceinline__ void dcross(const Dual a[3], const Dual b[3], Dual o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// trig in double, rounded once to fp32 (bit-identical to the oracle's sin32 / cos32)
+__device__ __forceinline__ void sincos32(float a, float* s, float* c) {
+  double sd, cd;
+  sincos((double)a, &sd, &cd);
+  *s = (float)sd;
+  *c = (float)cd;
+}
+
+// look_at_rotation + T = -R^T C  (pytorch3d renderer/cameras.py; environment.py:367-368)
+__device__ void look_at_store(const Dual C[3], float* __restrict__ cam) {
+  Dual up[3] = {mk(0.f), mk(1.f), mk(0.f)};
+  Dual mC[3] = {mk(0.f) - C[0], mk(0.f) - C[1], mk(0.f) - C[2]};
+  Dual x[3], y[3], z[3], t[3];
+  dnormalize(mC, 1e-5f, z);
+  dcross(up, z, t);
+  dnormalize(t, 1e-5f, x);
+  dcross(z, x, t);
+  dnormalize(t, 1e-5f, y);
+  if (fabsf(x[0].v) <= 5e-3f && fabsf(x[1].v) <= 5e-3f && fabsf(x[2].v) <= 5e-3f) {
+    dcross(y, z, t);
+    dnormalize(t, 1e-5f, x);
+  }
+  Dual T[3];
+  T[0] = -((x[0] * C[0] + x[1] * C[1]) + x[2] * C[2]);
+  T[1] = -((y[0] * C[0] + y[1] * C[1]) + y[2] * C[2]);
+  T[2] = -((z[0] * C[0] + z[1] * C[1]) + z[2] * C[2]);
+  // block 0: values, block 1: d/d_el, block 2: d/d_az ; each [R(9) T(3) C(3) pad]
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    cam[i * 3 + 0] = x[i].v;  cam[16 + i * 3 + 0] = x[i].d0;  cam[32 + i * 3 + 0] = x[i].d1;
+    cam[i * 3 + 1] = y[i].v;  cam[16 + i * 3 + 1] = y[i].d0;  cam[32 + i * 3 + 1] = y[i].d1;
+    cam[i * 3 + 2] = z[i].v;  cam[16 + i * 3 + 2] = z[i].d0;  cam[32 + i * 3 + 2] = z[i].d1;
+    cam[9 + i] = T[i].v;      cam[16 + 9 + i] = T[i].d0;      cam[32 + 9 + i] = T[i].d1;
+    cam[12 + i] = C[i].v;     cam[16 + 12 + i] = C[i].d0;     cam[32 + 12 + i] = C[i].d1;
+  }
+  cam[15] = 0.f; cam[31] = 0.f; cam[47] = 0.f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel 1a: pose
+// ----------------------------------------------------------------------------------------------
+// mode 0: step (environment.py:356-365), mode 1: look_at_view_transform (environment.py:308)
+__global__ void pose_kernel(int n, int mode, float step_size, const float* __restrict__ action,
+                            float* __restrict__ el_p, float* __restrict__ az_p,
+                            const float* __restrict__ radius_p, float* __restrict__ cam,
+                            float* __restrict__ position, uint32_t* __restrict__ status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  if (status) status[e] = 0u;
+  float el = el_p[e], az = az_p[e];
+  const float r = radius_p[e];
+  Dual C[3];
+  if (mode == 0) {
+    float a0 = action[2 * e + 0], a1 = action[2 * e + 1];
+    const float nrm = sqrtf(a0 * a0 + a1 * a1);
+    if (nrm != 0.f) {
+      a0 = a0 / nrm;
+      a1 = a1 / nrm;
+    }
+    el = el + a0 * step_size;
+    az = az + a1 * step_size;
+    el_p[e] = el;
+    az_p[e] = az;
+    float se, ce, sa, ca;
+    sincos32(el, &se, &ce);
+    sincos32(az, &sa, &ca);
+    const Dual sin_az{sa, 0.f, ca}, cos_az{ca, 0.f, -sa}, sin_el{se, ce, 0.f}, cos_el{ce, -se, 0.f};
+    const Dual rs = mk(r) * sin_az;
+    C[0] = rs * cos_el;
+    C[1] = rs * sin_el;
+    C[2] = mk(r) * cos_az;
+  } else {
+    float se, ce, sa, ca;
+    sincos32(el, &se, &ce);
+    sincos32(az, &sa, &ca);
+    const Dual sin_az{sa, 0.f, ca}, cos_az{ca, 0.f, -sa}, sin_el{se, ce, 0.f}, cos_el{ce, -se, 0.f};
+    const Dual dc = mk(r) * cos_el;
+    C[0] = dc * sin_az;
+    C[1] = mk(r) * sin_el;
+    C[2] = dc * cos_az;
+  }
+  look_at_store(C, cam + (size_t)e * OCCL_CAM_STRIDE);
+  if (position) {
+    position[3 * e + 0] = C[0].v;
+    position[3 * e + 1] = C[1].v;
+    position[3 * e + 2] = C[2].v;
+  }
+}
+
+__global__ void pose_set_kernel(int n, const float* __restrict__ R, const float* __restrict__ T,
+                                const float* __restrict__ C, float* __restrict__ cam) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float* c = cam + (size_t)e * OCCL_CAM_STRIDE;
+  for (int i = 0; i < OCCL_CAM_STRIDE; ++i) c[i] = 0.f;
+  for (int i = 0; i < 9; ++i) c[i] = R[9 * e + i];
+  for (int i = 0; i < 3; ++i) {
+    c[9 + i] = T[3 * e + i];
+    c[12 + i] = C[3 * e + i];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel 1b: projection
+// ----------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void project_kernel(long long total, int V, const float* __restrict__ cam,
+                               const float* __restrict__ verts, long long verts_stride, float s,
+                               float z_clip, float4* __restrict__ vproj, float4* __restrict__ vtan,
+                               uint32_t* __restrict__ status) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int e = (int)(idx / V);
+  const int v = (int)(idx - (long long)e * V);
+  const float* __restrict__ c = cam + (size_t)e * OCCL_CAM_STRIDE;
+  const float* __restrict__ p = verts + (size_t)e * verts_stride + (size_t)v * 3;
+  const float x = __ldg(p + 0), y = __ldg(p + 1), z = __ldg(p + 2);
+  // X_view = X_world R + T   (row-vector convention, left-to-right sums)
+  const float xv = ((x * __ldg(c + 0) + y * __ldg(c + 3)) + z * __ldg(c + 6)) + __ldg(c + 9);
+  const float yv = ((x * __ldg(c + 1) + y * __ldg(c + 4)) + z * __ldg(c + 7)) + __ldg(c + 10);
+  const float zv = ((x * __ldg(c + 2) + y * __ldg(c + 5)) + z * __ldg(c + 8)) + __ldg(c + 11);
+  const float xn = (s * xv) / zv;
+  const float yn = (s * yv) / zv;
+  vproj[idx] = make_float4(xn, yn, zv, 0.f);
+  if (zv < z_clip && status) atomicOr(status + e, OCCL_ST_ZCLIP);
+  if (GRAD) {
+    float t[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float* __restrict__ d = c + 16 * (k + 1);
+      const float dxv = x * __ldg(d + 0) + y * __ldg(d + 3) + z * __ldg(d + 6) + __ldg(d + 9);
+      const float dyv = x * __ldg(d + 1) + y * __ldg(d + 4) + z * __ldg(d + 7) + __ldg(d + 10);
+      const float dzv = x * __ldg(d + 2) + y * __ldg(d + 5) + z * __ldg(d + 8) + __ldg(d + 11);
+      t[2 * k + 0] = s * (dxv - (xv / zv) * dzv) / zv;
+      t[2 * k + 1] = s * (dyv - (yv / zv) * dzv) / zv;
+    }
+    vtan[idx] = make_float4(t[0], t[1], t[2], t[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel 2-5: tile rasteriser
+// ----------------------------------------------------------------------------------------------
+struct RasterParams {
+  int S, n_obj, V, F, K, cull;
+  int obj_face_start[OCCL_MAX_OBJ + 1];
+  int tile_w, tile_h, tiles_x, tiles_y;
+  float blur, bbox_r, sigma;
+  float light[3];
+  const float4* vproj;
+  const float4* vtan;
+  const float* verts;
+  long long verts_stride;
+  const int* faces;
+  long long faces_stride;
+  const float* cam;
+  Partial* partials;
+  // outputs
+  float* obs;
+  float* occl;
+  float* alphas;
+  int* pix_to_face;
+  float* bary;
+  int* nhits;
+  uint32_t* status;
+};
+
+struct FaceGeo {
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+  float area;  // (float)((double)EdgeFunction(v2, v0, v1) + kEpsilon)
+};
+
+struct PairResult {
+  float b0, b1, b2;  // perspective-corrected, unclipped barycentrics
+  float dist;        // squared NDC distance to the nearest edge
+  float t;           // clamped parameter on the nearest edge
+  int edge;          // 0: v0v1, 1: v0v2, 2: v1v2
+  bool inside;
+};
+
+__device__ __forceinline__ float seg_dist(float px, float py, float ax, float ay, float bx, float by,
+                                          float* tt_out) {
+  // PointLineDistanceForward
+  const float bax = bx - ax, bay = by - ay;
+  const float l2 = bax * bax + bay * bay;
+  if (l2 <= 1e-8f) {  // float form of (double)l2 <= 1e-8
+    const float dx = px - bx, dy = py - by;
+    *tt_out = 1.0f;
+    return dx * dx + dy * dy;
+  }
+  const float t = (bax * (px - ax) + bay * (py - ay)) / l2;
+  const float tt = fminf(fmaxf(t, 0.0f), 1.0f);
+  const float qx = ax + tt * bax, qy = ay + tt * bay;
+  const float dx = px - qx, dy = py - qy;
+  *tt_out = tt;
+  return dx * dx + dy * dy;
+}
+
+__device__ __forceinline__ void bary_persp(const FaceGeo& g, float px, float py, float* b0, float* b1,
+                                           float* b2) {
+  const float e0 = (px - g.x1) * (g.y2 - g.y1) - (py - g.y1) * (g.x2 - g.x1);
+  const float e1 = (px - g.x2) * (g.y0 - g.y2) - (py - g.y2) * (g.x0 - g.x2);
+  const float e2 = (px - g.x0) * (g.y1 - g.y0) - (py - g.y0) * (g.x1 - g.x0);
+  const float w0 = e0 / g.area, w1 = e1 / g.area, w2 = e2 / g.area;
+  const float t0 = w0 * g.z1 * g.z2;
+  const float t1 = g.z0 * w1 * g.z2;
+  const float t2 = g.z0 * g.z1 * w2;
+  const float den = fmaxf(t0 + t1 + t2, 1e-8f);
+  *b0 = t0 / den;
+  *b1 = t1 / den;
+  *b2 = t2 / den;
+}
+
+__device__ __forceinline__ PairResult eval_pair(const FaceGeo& g, float px, float py) {
+  PairResult r;
+  bary_persp(g, px, py, &r.b0, &r.b1, &r.b2);
+  r.inside = r.b0 > 0.f && r.b1 > 0.f && r.b2 > 0.f;
+  float t01, t02, t12;
+  const float d01 = seg_dist(px, py, g.x0, g.y0, g.x1, g.y1, &t01);
+  const float d02 = seg_dist(px, py, g.x0, g.y0, g.x2, g.y2, &t02);
+  const float d12 = seg_dist(px, py, g.x1, g.y1, g.x2, g.y2, &t12);
+  r.dist = fminf(fminf(d01, d02), d12);
+  if (d01 <= d02 && d01 <= d12) {
+    r.edge = 0;
+    r.t = t01;
+  } else if (d02 <= d01 && d02 <= d12) {
+    r.edge = 1;
+    r.t = t02;
+  } else {
+    r.edge = 2;
+    r.t = t12;
+  }
+  return r;
+}
+
+// clipped-barycentric depth used to order the K nearest soft hits (BarycentricClipForward)
+__device__ __forceinline__ float pz_clipped(const FaceGeo& g, float b0, float b1, float b2) {
+  float c0 = b0 > 0.f ? b0 : 0.f, c1 = b1 > 0.f ? b1 : 0.f, c2 = b2 > 0.f ? b2 : 0.f;
+  const float s = fmaxf(c0 + c1 + c2, 1e-5f);
+  c0 = c0 / s;
+  c1 = c1 / s;
+  c2 = c2 / s;
+  return c0 * g.z0 + c1 * g.z1 + c2 * g.z2;
+}
+
+__device__ __forceinline__ float soft_prob(float signed_dist, float sigma) {
+  // sigmoid(-dists / sigma)                                          
+  const float x = -signed_dist / sigma;
+  return 1.0f / (1.0f + expf(-x));
+}
+
+// Exact pixel range of an NDC interval [lo, hi]: pixels whose centre c satisfies !(c>hi) && !(c<lo).
+// Pixel centres DEcrease with the index: c(i) = pix_to_ndc(S-1-i).
+__device__ __forceinline__ void ndc_range_to_pixels(float lo, float hi, int S, int* i0, int* i1) {
+  const float fS = (float)S;
+  float e0 = ceilf(((1.0f - hi) * fS - 1.0f) * 0.5f) - 1.0f;
+  float e1 = floorf(((1.0f - lo) * fS - 1.0f) * 0.5f) + 1.0f;
+  e0 = fminf(fmaxf(e0, 0.0f), fS);
+  e1 = fminf(fmaxf(e1, -1.0f), fS - 1.0f);
+  int a = (int)e0, b = (int)e1;
+  if (!(e0 == e0)) a = 0;
+  if (!(e1 == e1)) b = S - 1;
+  while (a < S && pix_to_ndc(S - 1 - a, S) > hi) ++a;
+  while (a > 0 && !(pix_to_ndc(S - 1 - (a - 1), S) > hi)) --a;
+  while (b >= 0 && pix_to_ndc(S - 1 - b, S) < lo) --b;
+  while (b < S - 1 && !(pix_to_ndc(S - 1 - (b + 1), S) < lo)) ++b;
+  *i0 = a;
+  *i1 = b;
+}
+
+struct FaceSetup {
+  FaceGeo g;
+  bool live;
+  int sx0, sx1, sy0, sy1;  // soft (blur-expanded) pixel range, image coordinates
+  int hx0, hx1, hy0, hy1;  // hard (blur = 0) pixel range
+  float xmin, xmax, ymin, ymax;  // blur-expanded NDC bounding box
+};
+
+// Pixel-independent part of CheckPixelInsideFace: culls + the two bounding boxes.
+template <bool RANGES>
+__device__ __forceinline__ void setup_face(const float4 a, const float4 b, const float4 c, int S,
+                                           float bbox_r, int cull, FaceSetup* fs) {
+  FaceGeo& g = fs->g;
+  g.x0 = a.x; g.y0 = a.y; g.z0 = a.z;
+  g.x1 = b.x; g.y1 = b.y; g.z1 = b.z;
+  g.x2 = c.x; g.y2 = c.y; g.z2 = c.z;
+  // face_area = EdgeFunctionForward(v0, v1, v2)
+  const float face_area = (g.x0 - g.x1) * (g.y2 - g.y1) - (g.y0 - g.y1) * (g.x2 - g.x1);
+  const float zmax = fmaxf(fmaxf(g.z0, g.z1), g.z2);
+  const float zmin = fminf(fminf(g.z0, g.z1), g.z2);
+  bool skip = zmax < 0.f;
+  skip |= (cull && face_area < 0.f);
+  skip |= ((double)face_area <= 1e-8 && (double)face_area >= -1e-8);
+  skip |= ((double)zmin < 1e-8);
+  fs->live = !skip;
+  if (skip) return;
+  // area = EdgeFunctionForward(v2, v0, v1) + kEpsilon   (kEpsilon is a double)
+  const float e = (g.x2 - g.x0) * (g.y1 - g.y0) - (g.y2 - g.y0) * (g.x1 - g.x0);
+  g.area = (float)((double)e + 1e-8);
+  const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
+  const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
+  fs->xmin = xlo - bbox_r; fs->xmax = xhi + bbox_r;
+  fs->ymin = ylo - bbox_r; fs->ymax = yhi + bbox_r;
+  if (!RANGES) return;
+  ndc_range_to_pixels(xlo - bbox_r, xhi + bbox_r, S, &fs->sx0, &fs->sx1);
+  ndc_range_to_pixels(ylo - bbox_r, yhi + bbox_r, S, &fs->sy0, &fs->sy1);
+  ndc_range_to_pixels(xlo - 0.0f, xhi + 0.0f, S, &fs->hx0, &fs->hx1);
+  ndc_range_to_pixels(ylo - 0.0f, yhi + 0.0f, S, &fs->hy0, &fs->hy1);
+}
+
+__device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
+  int o = 0;
+#pragma unroll
+  for (int i = 1; i < OCCL_MAX_OBJ; ++i)
+    if (i < p.n_obj && f >= p.obj_face_start[i]) o = i;
+  return o;
+}
+
+// soft accumulator word: low 32 bits = running product of (1 - prob) as float bits,
+// high 32 bits = hit count (bits 0..30) | hard-covered flag (bit 31)
+__device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float q, bool covered) {
+  unsigned long long old = *slot, assumed;
+  do {
+    assumed = old;
+    const float pr = __uint_as_float((unsigned)(assumed & 0xffffffffull)) * q;
+    unsigned hi = (unsigned)(assumed >> 32) + 1u;
+    if (covered) hi |= 0x80000000u;
+    const unsigned long long nw = ((unsigned long long)hi << 32) | (unsigned long long)__float_as_uint(pr);
+    old = atomicCAS(slot, assumed, nw);
+  } while (old != assumed);
+}
+
+struct TileSmem {
+  unsigned long long* hard;  // [tpx]      (z bits << 32) | packed face index ; ~0 = background
+  unsigned long long* soft;  // [n_obj][tpx]
+  float* gacc;               // [n_obj][2][tpx]  (GRAD)
+  float* ndc_x;              // [tile_w]
+  float* ndc_y;              // [tile_h]
+  uint32_t* list;            // [LIST_CAP][REC_WORDS]  (aliased by the top-K selection buffers)
+};
+
+template <bool GRAD>
+__device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, int tpx,
+                                                   const uint32_t* __restrict__ rec, int env, int lane,
+                                                   int nlanes) {
+  FaceGeo g;
+  g.x0 = __uint_as_float(rec[0]); g.y0 = __uint_as_float(rec[1]); g.z0 = __uint_as_float(rec[2]);
+  g.x1 = __uint_as_float(rec[3]); g.y1 = __uint_as_float(rec[4]); g.z1 = __uint_as_float(rec[5]);
+  g.x2 = __uint_as_float(rec[6]); g.y2 = __uint_as_float(rec[7]); g.z2 = __uint_as_float(rec[8]);
+  g.area = __uint_as_float(rec[9]);
+  const int fidx = (int)rec[10];
+  const uint32_t sb = rec[11], hb = rec[12];
+  const int lx0 = sb & 0xff, lx1 = (sb >> 8) & 0xff, ly0 = (sb >> 16) & 0xff, ly1 = (sb >> 24) & 0xff;
+  const int hx0 = hb & 0xff, hx1 = (hb >> 8) & 0xff, hy0 = (hb >> 16) & 0xff, hy1 = (hb >> 24) & 0xff;
+  const int obj = obj_of_face(p, fidx);
+  const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
+  const int n = w * h;
+  float4 ta, tb, tc;
+  if (GRAD) {
+    const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+    ta = __ldg(vt + rec[13]);
+    tb = __ldg(vt + rec[14]);
+    tc = __ldg(vt + rec[15]);
+  }
+  unsigned long long* soft = sm.soft + (size_t)obj * tpx;
+  for (int i = lane; i < n; i += nlanes) {
+    const int ry = i / w;
+    const int rx = i - ry * w;
+    const int lx = lx0 + rx, ly = ly0 + ry;
+    const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
+    const PairResult r = eval_pair(g, px, py);
+    if (!r.inside && r.dist >= p.blur) continue;
+    const int pix = ly * p.tile_w + lx;
+    const float sd = r.inside ? -r.dist : r.dist;
+    const float prob = soft_prob(sd, p.sigma);
+    const bool hard_ok = r.inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
+    soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
+    if (hard_ok) {
+      const float pz = r.b0 * g.z0 + r.b1 * g.z1 + r.b2 * g.z2;
+      if (!(pz < 0.f)) {
+        const unsigned long long key =
+            ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)fidx;
+        atomicMin(sm.hard + pix, key);
+      }
+    }
+    if (GRAD) {
+      // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
+      float ax, ay, bx, by;
+      float4 da, db;
+      if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+      else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+      else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+      const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
+      const float sgn = r.inside ? -1.f : 1.f;
+      const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+      const float wa = 1.f - r.t, wb = r.t;
+      const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
+      const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
+      const float k = prob / p.sigma;
+      float* ga = sm.gacc + (size_t)obj * 2 * tpx;
+      atomicAdd(ga + pix, k * dsd_el);
+      atomicAdd(ga + tpx + pix, k * dsd_az);
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(OCCL_THREADS)
+raster_kernel(const RasterParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_tiles = p.tiles_x * p.tiles_y;
+  const int env = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - env * n_tiles;
+  const int tx0 = (tile % p.tiles_x) * p.tile_w;
+  const int ty0 = (tile / p.tiles_x) * p.tile_h;
+  const int tpx = p.tile_w * p.tile_h;
+  const int S = p.S;
+
+  TileSmem sm;
+  {
+    unsigned char* q = smem_raw;
+    sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
+    sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
+    sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * LIST_CAP * REC_WORDS;
+    sm.gacc = (float*)q;               if (GRAD) q += sizeof(float) * 2 * tpx * p.n_obj;
+    sm.ndc_x = (float*)q;              q += sizeof(float) * p.tile_w;
+    sm.ndc_y = (float*)q;
+  }
+  __shared__ int s_list_n, s_next, s_big_n, s_ovf_n, s_hit_n;
+  __shared__ int s_big[LIST_CAP];
+  __shared__ int s_ovf[OVF_CAP];
+  __shared__ double s_red[OCCL_WARPS][4];
+  __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
+
+  // ---- init accumulators -------------------------------------------------------------------
+  for (int i = tid; i < tpx; i += OCCL_THREADS) sm.hard[i] = ~0ull;
+  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = (unsigned long long)__float_as_uint(1.0f);
+  if (GRAD)
+    for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
+  for (int i = tid; i < p.tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
+  for (int i = tid; i < p.tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
+  if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_ovf_n = 0; s_hit_n = 0; }
+  __syncthreads();
+
+  const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
+  const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
+
+  // ---- face scan -> compacted list -> scatter ------------------------------------------------
+  for (int base = 0; base < p.F; base += SCAN_CHUNK) {
+    const int f = base + tid;
+    bool keep = false;
+    FaceSetup fs;
+    int i0 = 0, i1 = 0, i2 = 0;
+    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (f < p.F) {
+      i0 = __ldg(faces + 3 * f + 0);
+      i1 = __ldg(faces + 3 * f + 1);
+      i2 = __ldg(faces + 3 * f + 2);
+      setup_face<true>(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), S, p.bbox_r, p.cull, &fs);
+      if (fs.live) {
+        cx0 = max(fs.sx0, tx0);  cx1 = min(fs.sx1, tx0 + p.tile_w - 1);
+        cy0 = max(fs.sy0, ty0);  cy1 = min(fs.sy1, ty0 + p.tile_h - 1);
+        keep = cx0 <= cx1 && cy0 <= cy1;
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int slot0 = 0;
+    if (lane == 0 && bal) slot0 = atomicAdd(&s_list_n, __popc(bal));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (keep) {
+      const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+      uint32_t* rec = sm.list + slot * REC_WORDS;
+      rec[0] = __float_as_uint(fs.g.x0); rec[1] = __float_as_uint(fs.g.y0); rec[2] = __float_as_uint(fs.g.z0);
+      rec[3] = __float_as_uint(fs.g.x1); rec[4] = __float_as_uint(fs.g.y1); rec[5] = __float_as_uint(fs.g.z1);
+      rec[6] = __float_as_uint(fs.g.x2); rec[7] = __float_as_uint(fs.g.y2); rec[8] = __float_as_uint(fs.g.z2);
+      rec[9] = __float_as_uint(fs.g.area);
+      rec[10] = (uint32_t)f;
+      rec[11] = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
+                ((uint32_t)(cy1 - ty0) << 24);
+      // hard range clipped to the tile; empty -> x0 = 255, x1 = 0
+      int hx0 = max(fs.hx0, tx0) - tx0, hx1 = min(fs.hx1, tx0 + p.tile_w - 1) - tx0;
+      int hy0 = max(fs.hy0, ty0) - ty0, hy1 = min(fs.hy1, ty0 + p.tile_h - 1) - ty0;
+      if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
+      rec[12] = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
+      rec[13] = (uint32_t)i0; rec[14] = (uint32_t)i1; rec[15] = (uint32_t)i2;
+      if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > BIG_FACE_PX) s_big[atomicAdd(&s_big_n, 1)] = slot;
+    }
+    __syncthreads();
+    const bool last = base + SCAN_CHUNK >= p.F;
+    const int n = s_list_n;
+    __syncthreads();  // everyone has read the count before the next round may append
+    if (n > LIST_CAP - SCAN_CHUNK || last) {
+      // small faces: one warp per face, dynamically scheduled
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(&s_next, 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const uint32_t* rec = sm.list + i * REC_WORDS;
+        const uint32_t sb = rec[11];
+        const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
+        if (npx > BIG_FACE_PX) continue;
+        raster_face_pixels<GRAD>(p, sm, tpx, rec, env, lane, 32);
+      }
+      __syncthreads();
+      // big faces: the whole CTA on one face at a time
+      const int nb = s_big_n;
+      for (int b = 0; b < nb; ++b) raster_face_pixels<GRAD>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, env, tid, OCCL_THREADS);
+      __syncthreads();
+      if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; }
+      __syncthreads();
+    }
+  }
+
+  // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
+  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
+    const unsigned cnt = (unsigned)(sm.soft[i] >> 32) & 0x7fffffffu;
+    if ((int)cnt > p.K) {
+      const int s = atomicAdd(&s_ovf_n, 1);
+      if (s < OVF_CAP) s_ovf[s] = i;
+    }
+  }
+  __syncthreads();
+  int n_ovf = s_ovf_n;
+  if (n_ovf > 0) {
+    if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW | (n_ovf > OVF_CAP ? OCCL_ST_OVFCAP : 0u));
+    n_ovf = min(n_ovf, OVF_CAP);
+    // selection buffers alias the (now idle) face list
+    unsigned long long* hkey = (unsigned long long*)sm.list;            // [HIT_CAP]
+    float* hq = (float*)(hkey + HIT_CAP);                               // [HIT_CAP]
+    float* hg = hq + HIT_CAP;                                           // [2][HIT_CAP] (GRAD)
+    // deterministic order of the overflow list (atomicAdd order is not): sort small list by value
+    if (tid == 0) {
+      for (int a = 1; a < n_ovf; ++a) {
+        const int v = s_ovf[a];
+        int b = a - 1;
+        while (b >= 0 && s_ovf[b] > v) { s_ovf[b + 1] = s_ovf[b]; --b; }
+        s_ovf[b + 1] = v;
+      }
+    }
+    __syncthreads();
+    for (int oi = 0; oi < n_ovf; ++oi) {
+      const int slot = s_ovf[oi];
+      const int obj = slot / tpx;
+      const int pix = slot - obj * tpx;
+      const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
+      const int xi = tx0 + lx, yi = ty0 + ly;
+      const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
+      if (tid == 0) s_hit_n = 0;
+      __syncthreads();
+      for (int f = p.obj_face_start[obj] + tid; f < p.obj_face_start[obj + 1]; f += OCCL_THREADS) {
+        const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+        FaceSetup fs;
+        setup_face<false>(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), S, p.bbox_r, p.cull, &fs);
+        if (!fs.live || px > fs.xmax || px < fs.xmin || py > fs.ymax || py < fs.ymin) continue;
+        const PairResult r = eval_pair(fs.g, px, py);
+        if (!r.inside && r.dist >= p.blur) continue;
+        const float pz = pz_clipped(fs.g, r.b0, r.b1, r.b2);
+        const float sd = r.inside ? -r.dist : r.dist;
+        const float prob = soft_prob(sd, p.sigma);
+        const int h = atomicAdd(&s_hit_n, 1);
+        if (h < HIT_CAP) {
+          hkey[h] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
+          hq[h] = 1.0f - prob;
+          if (GRAD) {
+            const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+            const float4 ta = __ldg(vt + i0), tb = __ldg(vt + i1), tc = __ldg(vt + i2);
+            float ax, ay, bx, by;
+            float4 da, db;
+            const FaceGeo& g = fs.g;
+            if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+            else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+            else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+            const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
+            const float sgn = r.inside ? -1.f : 1.f;
+            const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+            const float wa = 1.f - r.t, wb = r.t;
+            const float k = prob / p.sigma;
+            hg[h] = k * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+            hg[HIT_CAP + h] = k * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+          }
+        }
+      }
+      __syncthreads();
+      int nh = s_hit_n;
+      if (nh > HIT_CAP) {
+        if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
+        nh = HIT_CAP;
+      }
+      // rank of every hit by (pz, face) ; the K smallest survive. Products are taken in rank order.
+      __shared__ float s_sel_q[128];
+      __shared__ float s_sel_g[2][128];
+      const int Ksel = min(p.K, 128);
+      for (int a = tid; a < nh; a += OCCL_THREADS) {
+        const unsigned long long ka = hkey[a];
+        int rank = 0;
+        for (int b = 0; b < nh; ++b) rank += hkey[b] < ka;
+        if (rank < Ksel) {
+          s_sel_q[rank] = hq[a];
+          if (GRAD) { s_sel_g[0][rank] = hg[a]; s_sel_g[1][rank] = hg[HIT_CAP + a]; }
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const int m = min(nh, Ksel);
+        float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+        for (int a = lane; a < m; a += 32) {
+          pr = pr * s_sel_q[a];
+          if (GRAD) { g0 += s_sel_g[0][a]; g1 += s_sel_g[1][a]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+          if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+        }
+        if (lane == 0) {
+          const unsigned long long old = sm.soft[slot];
+          sm.soft[slot] = (old & 0xffffffff00000000ull) | (unsigned long long)__float_as_uint(pr);
+          if (GRAD) {
+            sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
+            sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
+  const float* __restrict__ cam = p.cam + (size_t)env * OCCL_CAM_STRIDE;
+  const float* __restrict__ wv = p.verts + (size_t)env * p.verts_stride;
+  const float camx = __ldg(cam + 12), camy = __ldg(cam + 13), camz = __ldg(cam + 14);
+  const size_t npix = (size_t)S * S;
+  double acc_loss = 0.0, acc_obj = 0.0, acc_g0 = 0.0, acc_g1 = 0.0;
+  int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
+  for (int i = tid; i < tpx; i += OCCL_THREADS) {
+    const int ly = i / p.tile_w, lx = i - ly * p.tile_w;
+    const int xi = tx0 + lx, yi = ty0 + ly;
+    if (xi >= S || yi >= S) continue;
+    const size_t pix = (size_t)yi * S + xi;
+    float A[OCCL_MAX_OBJ], PR[OCCL_MAX_OBJ];
+#pragma unroll
+    for (int o = 0; o < OCCL_MAX_OBJ; ++o) {
+      A[o] = 0.f;
+      PR[o] = 1.f;
+      if (o < p.n_obj) {
+        const unsigned long long w = sm.soft[(size_t)o * tpx + i];
+        PR[o] = __uint_as_float((unsigned)(w & 0xffffffffull));
+        A[o] = 1.0f - PR[o];
+        const unsigned hi = (unsigned)(w >> 32);
+        ncov[o] += (int)(hi >> 31);
+        if (p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
+        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & 0x7fffffffu);
+      }
+    }
+    float occl = 0.f, objs = 0.f;
+#pragma unroll
+    for (int a = 0; a < OCCL_MAX_OBJ; ++a) {
+      if (a < p.n_obj) objs = objs + A[a];
+#pragma unroll
+      for (int b = a + 1; b < OCCL_MAX_OBJ; ++b)
+        if (b < p.n_obj) occl = occl + A[a] * A[b];
+    }
+    p.occl[(size_t)env * npix + pix] = occl;
+    acc_loss += (double)occl * (double)occl;
+    acc_obj += (double)objs * (double)objs;
+    if (GRAD) {
+      // dA_o = -(1 - A_o) * G_o ; d loss = 2 occl * sum_o (sum_{j != o} A_j) dA_o
+      float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+      for (int o = 0; o < OCCL_MAX_OBJ; ++o) {
+        if (o < p.n_obj) {
+          const float others = objs - A[o];
+          const float c = -PR[o] * others;
+          g0 += c * sm.gacc[(size_t)o * 2 * tpx + i];
+          g1 += c * sm.gacc[(size_t)o * 2 * tpx + tpx + i];
+        }
+      }
+      acc_g0 += 2.0 * (double)occl * (double)g0;
+      acc_g1 += 2.0 * (double)occl * (double)g1;
+    }
+    // observation: nearest scene face, flat shading, background (1,1,1), depth channel
+    const unsigned long long key = sm.hard[i];
+    float rgb = 1.0f, depth = -1.0f;
+    int pf = -1;
+    float b0 = -1.f, b1 = -1.f, b2 = -1.f;
+    if (key != ~0ull) {
+      pf = (int)(unsigned)(key & 0xffffffffull);
+      depth = __uint_as_float((unsigned)(key >> 32));
+      nvis[obj_of_face(p, pf)] += 1;
+      const int i0 = __ldg(faces + 3 * pf + 0), i1 = __ldg(faces + 3 * pf + 1), i2 = __ldg(faces + 3 * pf + 2);
+      const float4 a = __ldg(vp + i0), b = __ldg(vp + i1), c = __ldg(vp + i2);
+      FaceGeo g;
+      g.x0 = a.x; g.y0 = a.y; g.z0 = a.z; g.x1 = b.x; g.y1 = b.y; g.z1 = b.z; g.x2 = c.x; g.y2 = c.y; g.z2 = c.z;
+      const float e = (g.x2 - g.x0) * (g.y1 - g.y0) - (g.y2 - g.y0) * (g.x1 - g.x0);
+      g.area = (float)((double)e + 1e-8);
+      bary_persp(g, sm.ndc_x[lx], sm.ndc_y[ly], &b0, &b1, &b2);
+      const float* w0 = wv + 3 * (size_t)i0;
+      const float* w1 = wv + 3 * (size_t)i1;
+      const float* w2 = wv + 3 * (size_t)i2;
+      float v0[3], e1[3], e2[3], ctr[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        v0[k] = __ldg(w0 + k);
+        const float q1 = __ldg(w1 + k), q2 = __ldg(w2 + k);
+        e1[k] = q1 - v0[k];
+        e2[k] = q2 - v0[k];
+        ctr[k] = ((v0[k] + q1) + q2) / 3.0f;
+      }
+      float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+      float nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+      nn = nn > 1e-6f ? nn : 1e-6f;
+      n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+      nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+      nn = nn > 1e-6f ? nn : 1e-6f;
+      n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+      float dir[3] = {p.light[0] - ctr[0], p.light[1] - ctr[1], p.light[2] - ctr[2]};
+      float view[3] = {camx - ctr[0], camy - ctr[1], camz - ctr[2]};
+      float dn = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+      dn = dn > 1e-6f ? dn : 1e-6f;
+      dir[0] = dir[0] / dn; dir[1] = dir[1] / dn; dir[2] = dir[2] / dn;
+      float vn = sqrtf((view[0] * view[0] + view[1] * view[1]) + view[2] * view[2]);
+      vn = vn > 1e-6f ? vn : 1e-6f;
+      view[0] = view[0] / vn; view[1] = view[1] / vn; view[2] = view[2] / vn;
+      const float cosang = (n[0] * dir[0] + n[1] * dir[1]) + n[2] * dir[2];
+      const float diffuse = 0.3f * (cosang > 0.f ? cosang : 0.f);
+      const float r0 = -dir[0] + 2.0f * (cosang * n[0]);
+      const float r1 = -dir[1] + 2.0f * (cosang * n[1]);
+      const float r2 = -dir[2] + 2.0f * (cosang * n[2]);
+      float al = (view[0] * r0 + view[1] * r1) + view[2] * r2;
+      al = (al > 0.f ? al : 0.f) * (cosang > 0.f ? 1.0f : 0.0f);
+      const float spec = 0.2f * powf(al, 64.0f);
+      const float texel = (b0 + b1) + b2;
+      rgb = (0.5f + diffuse) * texel + spec;
+    }
+    float* o = p.obs + (size_t)env * 4 * npix + pix;
+    o[0] = rgb;
+    o[npix] = rgb;
+    o[2 * npix] = rgb;
+    o[3 * npix] = depth;
+    if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = pf;
+    if (p.bary) {
+      float* bq = p.bary + ((size_t)env * npix + pix) * 3;
+      bq[0] = b0; bq[1] = b1; bq[2] = b2;
+    }
+  }
+  // block reduction, fixed order -> deterministic given the per-pixel values
+  acc_loss = warp_sum(acc_loss);
+  acc_obj = warp_sum(acc_obj);
+  if (GRAD) { acc_g0 = warp_sum(acc_g0); acc_g1 = warp_sum(acc_g1); }
+#pragma unroll
+  for (int o = 0; o < OCCL_MAX_OBJ; ++o) { ncov[o] = warp_sum_i(ncov[o]); nvis[o] = warp_sum_i(nvis[o]); }
+  if (lane == 0) {
+    s_red[warp][0] = acc_loss; s_red[warp][1] = acc_obj; s_red[warp][2] = acc_g0; s_red[warp][3] = acc_g1;
+#pragma unroll
+    for (int o = 0; o < OCCL_MAX_OBJ; ++o) { s_redi[warp][o] = ncov[o]; s_redi[warp][OCCL_MAX_OBJ + o] = nvis[o]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    Partial out;
+    out.loss = 0; out.objsq = 0; out.gl[0] = 0; out.gl[1] = 0;
+    for (int o = 0; o < OCCL_MAX_OBJ; ++o) { out.ncov[o] = 0; out.nvis[o] = 0; }
+    for (int w = 0; w < OCCL_WARPS; ++w) {
+      out.loss += s_red[w][0]; out.objsq += s_red[w][1]; out.gl[0] += s_red[w][2]; out.gl[1] += s_red[w][3];
+      for (int o = 0; o < OCCL_MAX_OBJ; ++o) { out.ncov[o] += s_redi[w][o]; out.nvis[o] += s_redi[w][OCCL_MAX_OBJ + o]; }
+    }
+    p.partials[(size_t)env * n_tiles + tile] = out;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel 6: per-env finalisation
+// ----------------------------------------------------------------------------------------------
+// mode 0: step (environment.py:381-392) ; mode 1: reset (:322-327) ; mode 2: render only
+__global__ void finalize_kernel(int n, int mode, int n_tiles, int n_obj, int norm_with_object_size,
+                                float done_threshold, float reward_done, float reward_step, float step_size,
+                                const Partial* __restrict__ partials, const float* __restrict__ action,
+                                float* __restrict__ full_reward, float* __restrict__ object_mass,
+                                float* __restrict__ reward, uint8_t* __restrict__ done,
+                                float* __restrict__ loss_out, int* __restrict__ n_covered,
+                                int* __restrict__ n_visible, float* __restrict__ grad_action) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double loss = 0.0, objsq = 0.0, g0 = 0.0, g1 = 0.0;
+  int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
+  const Partial* __restrict__ pp = partials + (size_t)e * n_tiles;
+  for (int t = 0; t < n_tiles; ++t) {
+    loss += pp[t].loss; objsq += pp[t].objsq; g0 += pp[t].gl[0]; g1 += pp[t].gl[1];
+    for (int o = 0; o < OCCL_MAX_OBJ; ++o) { ncov[o] += pp[t].ncov[o]; nvis[o] += pp[t].nvis[o]; }
+  }
+  const float lossf = (float)loss;
+  if (loss_out) loss_out[e] = lossf;
+  for (int o = 0; o < n_obj; ++o) {
+    if (n_covered) n_covered[e * n_obj + o] = ncov[o];
+    if (n_visible) n_visible[e * n_obj + o] = nvis[o];
+  }
+  if (mode == 2) return;
+  if (mode == 1) {
+    full_reward[e] = lossf;                                                  // :323
+    object_mass[e] = (norm_with_object_size ? (float)objsq : lossf) + 1.0f;  // :324
+    if (done) done[e] = (uint8_t)(!(lossf > done_threshold));                // :327 (no occlusion at reset)
+    return;
+  }
+  const float mass = object_mass[e];
+  float r = full_reward[e] - lossf;  // :382
+  full_reward[e] = lossf;            // :384
+  const bool fin = lossf < done_threshold;  // :386
+  r = r / mass;                             // :387
+  r = fin ? r + reward_done : r - reward_step;
+  reward[e] = r;
+  done[e] = (uint8_t)fin;
+  if (grad_action) {
+    // d reward / d(el, az) = -(d loss / d(el, az)) / mass ; (el, az) += step * a / |a|
+    const float ge = (float)(-g0 / (double)mass), ga = (float)(-g1 / (double)mass);
+    const float a0 = action[2 * e + 0], a1 = action[2 * e + 1];
+    const float nrm = sqrtf(a0 * a0 + a1 * a1);
+    if (nrm != 0.f) {
+      const float n0 = a0 / nrm, n1 = a1 / nrm;
+      const float dot = ge * n0 + ga * n1;
+      grad_action[2 * e + 0] = step_size * (ge - dot * n0) / nrm;
+      grad_action[2 * e + 1] = step_size * (ga - dot * n1) / nrm;
+    } else {
+      grad_action[2 * e + 0] = step_size * ge;
+      grad_action[2 * e + 1] = step_size * ga;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side: C-ABI
+// ----------------------------------------------------------------------------------------------
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_last_err, sizeof(g_last_err), "%s: %s", where, cudaGetErrorString(e));
+  return OCCL_E_CUDA;
+}
+#define CK(call, where)                                      \
+  do {                                                       \
+    cudaError_t _e = (call);                                 \
+    if (_e != cudaSuccess) return cuda_fail(_e, where);      \
+  } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t cam, vproj, vtan, partials, total;
+  int n_tiles;
+};
+
+static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
+  const size_t tpx = (size_t)c->tile_w * c->tile_h;
+  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * LIST_CAP * REC_WORDS;
+  if (with_grad) b += 4 * 2 * tpx * c->n_obj;
+  b += 4 * (size_t)(c->tile_w + c->tile_h);
+  return b;
+}
+
+extern "C" int occl_abi_version(void) { return OCCL_ABI_VERSION; }
+extern "C" const char* occl_last_cuda_error(void) { return g_last_err; }
+
+extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
+  if (!c) return OCCL_E_INVALID;
+  if (c->image_size < 1 || c->image_size > 4096) return OCCL_E_INVALID;
+  if (c->n_obj < 1 || c->n_obj > OCCL_MAX_OBJ) return OCCL_E_INVALID;
+  if (c->n_verts < 1 || c->n_faces < 1) return OCCL_E_INVALID;
+  if (c->faces_per_pixel < 1 || c->faces_per_pixel > 128) return OCCL_E_INVALID;
+  if (c->obj_face_start[0] != 0 || c->obj_face_start[c->n_obj] != c->n_faces) return OCCL_E_INVALID;
+  for (int i = 0; i < c->n_obj; ++i)
+    if (c->obj_face_start[i + 1] < c->obj_face_start[i]) return OCCL_E_INVALID;
+  if (!(c->blur_radius >= 0.f) || !(c->sigma > 0.f)) return OCCL_E_INVALID;
+  if (c->tile_w == 0 || c->tile_h == 0) {
+    const int S = c->image_size;
+    c->tile_w = S < 64 ? S : 64;
+    c->tile_h = S < 16 ? S : 16;
+  }
+  if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
+  if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
+  // the top-K selection buffers alias the face list
+  if ((size_t)HIT_CAP * (8 + 4 + 8) > (size_t)4 * LIST_CAP * REC_WORDS) return OCCL_E_INVALID;
+  return OCCL_OK;
+}
+
+static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
+  const int tx = (c->image_size + c->tile_w - 1) / c->tile_w;
+  const int ty = (c->image_size + c->tile_h - 1) / c->tile_h;
+  L->n_tiles = tx * ty;
+  size_t off = 0;
+  L->cam = off;      off = align_up(off + sizeof(float) * OCCL_CAM_STRIDE * (size_t)n, 256);
+  L->vproj = off;    off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
+  L->vtan = off;     if (with_grad) off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
+  L->partials = off; off = align_up(off + sizeof(Partial) * (size_t)n * L->n_tiles, 256);
+  L->total = off;
+  return 0;
+}
+
+extern "C" size_t occl_workspace_bytes(const OcclConfig* cfg, int n_envs, int with_grad) {
+  if (!cfg || n_envs < 1) return 0;
+  OcclConfig c = *cfg;
+  if (occl_config_resolve(&c, with_grad) != OCCL_OK) return 0;
+  WsLayout L;
+  ws_layout(&c, n_envs, with_grad, &L);
+  return L.total;
+}
+
+static int launch_pose(const OcclConfig* c, int n, int mode, const float* action, OcclState st, float* cam,
+                       float* position, uint32_t* status, cudaStream_t s) {
+  if (!st.elevation || !st.azimuth || !st.radius || !cam) return OCCL_E_INVALID;
+  if (mode == 0 && !action) return OCCL_E_INVALID;
+  pose_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, mode, c->step_size, action, st.elevation, st.azimuth, st.radius,
+                                             cam, position, status);
+  CK(cudaGetLastError(), "pose_kernel");
+  return OCCL_OK;
+}
+
+extern "C" int occl_pose_step(const OcclConfig* cfg, int n, const float* action, OcclState st, float* cam,
+                              void* stream) {
+  if (!cfg || n < 1) return OCCL_E_INVALID;
+  return launch_pose(cfg, n, 0, action, st, cam, nullptr, nullptr, (cudaStream_t)stream);
+}
+extern "C" int occl_pose_lookat(const OcclConfig* cfg, int n, OcclState st, float* cam, void* stream) {
+  if (!cfg || n < 1) return OCCL_E_INVALID;
+  return launch_pose(cfg, n, 1, nullptr, st, cam, nullptr, nullptr, (cudaStream_t)stream);
+}
+extern "C" int occl_pose_set(int n, const float* R, const float* T, const float* C, float* cam, void* stream) {
+  if (n < 1 || !R || !T || !C || !cam) return OCCL_E_INVALID;
+  pose_set_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, R, T, C, cam);
+  CK(cudaGetLastError(), "pose_set_kernel");
+  return OCCL_OK;
+}
+
+extern "C" int occl_project(const OcclConfig* cfg, int n, const float* cam, OcclScene sc, float* vproj, float* vtan,
+                            uint32_t* status, void* stream) {
+  if (!cfg || n < 1 || !cam || !sc.verts || !vproj) return OCCL_E_INVALID;
+  const long long total = (long long)n * cfg->n_verts;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (vtan)
+    project_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(total, cfg->n_verts, cam, sc.verts, sc.verts_env_stride,
+                                                                  cfg->proj_scale, cfg->z_clip, (float4*)vproj,
+                                                                  (float4*)vtan, status);
+  else
+    project_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(total, cfg->n_verts, cam, sc.verts, sc.verts_env_stride,
+                                                                   cfg->proj_scale, cfg->z_clip, (float4*)vproj, nullptr,
+                                                                   status);
+  CK(cudaGetLastError(), "project_kernel");
+  return OCCL_OK;
+}
+
+static int check_outputs(const OcclOutputs& o) {
+  if (!o.obs || !o.occl || !o.status) return OCCL_E_INVALID;
+  return OCCL_OK;
+}
+
+extern "C" int occl_raster(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace ws, OcclOutputs out, void* stream) {
+  if (!cfg || n < 1 || !sc.verts || !sc.faces || !ws.base) return OCCL_E_INVALID;
+  if (check_outputs(out) != OCCL_OK) return OCCL_E_INVALID;
+  const int grad = out.grad_action != nullptr;
+  OcclConfig c = *cfg;
+  int rc = occl_config_resolve(&c, grad);
+  if (rc != OCCL_OK) return rc;
+  WsLayout L;
+  ws_layout(&c, n, grad, &L);
+  if (ws.bytes < L.total) return OCCL_E_INVALID;
+  unsigned char* base = (unsigned char*)ws.base;
+  RasterParams p;
+  p.S = c.image_size; p.n_obj = c.n_obj; p.V = c.n_verts; p.F = c.n_faces; p.K = c.faces_per_pixel;
+  p.cull = c.cull_backfaces;
+  for (int i = 0; i <= OCCL_MAX_OBJ; ++i) p.obj_face_start[i] = i <= c.n_obj ? c.obj_face_start[i] : c.n_faces;
+  p.tile_w = c.tile_w; p.tile_h = c.tile_h;
+  p.tiles_x = (c.image_size + c.tile_w - 1) / c.tile_w;
+  p.tiles_y = (c.image_size + c.tile_h - 1) / c.tile_h;
+  p.blur = c.blur_radius; p.bbox_r = sqrtf(c.blur_radius); p.sigma = c.sigma;
+  p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
+  p.vproj = (const float4*)(base + L.vproj);
+  p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
+  p.verts = sc.verts; p.verts_stride = sc.verts_env_stride;
+  p.faces = sc.faces; p.faces_stride = sc.faces_env_stride;
+  p.cam = (const float*)(base + L.cam);
+  p.partials = (Partial*)(base + L.partials);
+  p.obs = out.obs; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
+  p.nhits = out.nhits; p.status = out.status;
+  const size_t smem = tile_smem_bytes(&c, grad);
+  const long long blocks = (long long)n * L.n_tiles;
+  if (blocks > 0x7fffffffLL) return OCCL_E_INVALID;
+  if (grad) {
+    CK(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    raster_kernel<true><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    CK(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    raster_kernel<false><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+  }
+  CK(cudaGetLastError(), "raster_kernel");
+  return OCCL_OK;
+}
+
+extern "C" int occl_finalize(const OcclConfig* cfg, int n, int mode, const float* action, OcclState st, OcclWorkspace ws,
+                             OcclOutputs out, void* stream) {
+  if (!cfg || n < 1 || !ws.base || mode < 0 || mode > 2) return OCCL_E_INVALID;
+  const int grad = out.grad_action != nullptr;
+  OcclConfig c = *cfg;
+  int rc = occl_config_resolve(&c, grad);
+  if (rc != OCCL_OK) return rc;
+  if (mode != 2 && (!st.full_reward || !st.object_mass)) return OCCL_E_INVALID;
+  if (mode == 0 && (!out.reward || !out.done)) return OCCL_E_INVALID;
+  if (mode == 0 && grad && !action) return OCCL_E_INVALID;
+  WsLayout L;
+  ws_layout(&c, n, grad, &L);
+  if (ws.bytes < L.total) return OCCL_E_INVALID;
+  unsigned char* base = (unsigned char*)ws.base;
+  finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, mode, L.n_tiles, c.n_obj, c.norm_with_object_size, c.done_threshold, c.reward_done, c.reward_step, c.step_size,
+      (const Partial*)(base + L.partials), action, st.full_reward, st.object_mass, out.reward, out.done, out.loss,
+      out.n_covered, out.n_visible, mode == 0 ? out.grad_action : nullptr);
+  CK(cudaGetLastError(), "finalize_kernel");
+  return OCCL_OK;
+}
+
+static int run_chain(const OcclConfig* cfg, int n, int mode, const float* action, const float* R, const float* T,
+                     const float* C, OcclScene sc, OcclState st, OcclWorkspace ws, OcclOutputs out, void* stream) {
+  if (!cfg || n < 1 || !ws.base) return OCCL_E_INVALID;
+  if (check_outputs(out) != OCCL_OK) return OCCL_E_INVALID;
+  const int grad = out.grad_action != nullptr;
+  OcclConfig c = *cfg;
+  int rc = occl_config_resolve(&c, grad);
+  if (rc != OCCL_OK) return rc;
+  WsLayout L;
+  ws_layout(&c, n, grad, &L);
+  if (ws.bytes < L.total) return OCCL_E_INVALID;
+  unsigned char* base = (unsigned char*)ws.base;
+  float* cam = (float*)(base + L.cam);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 2) {
+    CK(cudaMemsetAsync(out.status, 0, sizeof(uint32_t) * (size_t)n, s), "memset status");
+    rc = occl_pose_set(n, R, T, C, cam, stream);
+  } else {
+    rc = launch_pose(&c, n, mode, action, st, cam, out.position, out.status, s);
+  }
+  if (rc != OCCL_OK) return rc;
+  rc = occl_project(&c, n, cam, sc, (float*)(base + L.vproj), grad ? (float*)(base + L.vtan) : nullptr, out.status, stream);
+  if (rc != OCCL_OK) return rc;
+  rc = occl_raster(&c, n, sc, ws, out, stream);
+  if (rc != OCCL_OK) return rc;
+  return occl_finalize(&c, n, mode, action, st, ws, out, stream);
+}
+
+extern "C" int occl_step(const OcclConfig* cfg, int n, const float* action, OcclScene sc, OcclState st, OcclWorkspace ws,
+                         OcclOutputs out, void* stream) {
+  if (!action) return OCCL_E_INVALID;
+  return run_chain(cfg, n, 0, action, nullptr, nullptr, nullptr, sc, st, ws, out, stream);
+}
+extern "C" int occl_reset(const OcclConfig* cfg, int n, OcclScene sc, OcclState st, OcclWorkspace ws, OcclOutputs out,
+                          void* stream) {
+  OcclOutputs o = out;
+  o.grad_action = nullptr;
+  return run_chain(cfg, n, 1, nullptr, nullptr, nullptr, nullptr, sc, st, ws, o, stream);
+}
+extern "C" int occl_render(const OcclConfig* cfg, int n, const float* R, const float* T, const float* C, OcclScene sc,
+                           OcclWorkspace ws, OcclOutputs out, void* stream) {
+  if (!R || !T || !C) return OCCL_E_INVALID;
+  OcclOutputs o = out;
+  o.grad_action = nullptr;
+  OcclState st = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  return run_chain(cfg, n, 2, nullptr, R, T, C, sc, st, ws, o, stream);
+}

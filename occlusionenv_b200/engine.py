@@ -1,0 +1,173 @@
+"""Device-side engine: owns the HBM-resident scene, per-env state, workspace and output buffers of N
+environments and drives the C-ABI (include/occl_b200.h).  PyTorch is used for device memory and
+streams only; all arithmetic of the transition runs in libocclb200.so.
+
+Replaces, for N environments at once, what ``OcclusionEnv.reset`` / ``.step`` / ``.render`` do through
+pytorch3d (``/root/reference/environment.py:286-396``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .config import RasterConfig
+from .meshes import SceneMesh
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class OcclusionEngine:
+    def __init__(self, scene, n_envs: int, cfg: RasterConfig, device="cuda:0", debug_outputs: bool = False,
+                 per_env_scenes: Optional[list] = None):
+        if not torch.cuda.is_available():
+            raise L.OcclError("OcclusionEngine needs a CUDA device (there is no CPU fallback)")
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.n = int(n_envs)
+        self.cfg = cfg
+        self.S = cfg.image_size
+        if per_env_scenes is not None:
+            scene0 = per_env_scenes[0]
+            assert len(per_env_scenes) == self.n
+            for sc in per_env_scenes:
+                assert sc.verts.shape == scene0.verts.shape and sc.faces.shape == scene0.faces.shape
+                assert np.array_equal(sc.obj_face_start, scene0.obj_face_start)
+            verts = np.stack([sc.verts for sc in per_env_scenes])
+            faces = np.stack([sc.faces for sc in per_env_scenes])
+            self.scene = scene0
+            vstride, fstride = scene0.verts.size, scene0.faces.size
+        else:
+            self.scene = scene
+            verts, faces = scene.verts, scene.faces
+            vstride = fstride = 0
+        sc = self.scene
+        self.n_obj = sc.n_obj
+        self.verts = torch.from_numpy(np.ascontiguousarray(verts, np.float32)).to(self.device)
+        self.faces = torch.from_numpy(np.ascontiguousarray(faces, np.int32)).to(self.device)
+        c = L.OcclConfig()
+        c.image_size = cfg.image_size
+        c.n_obj = sc.n_obj
+        c.n_verts = sc.verts.shape[0]
+        c.n_faces = sc.faces.shape[0]
+        for i in range(L.OCCL_MAX_OBJ + 1):
+            c.obj_face_start[i] = int(sc.obj_face_start[min(i, sc.n_obj)])
+        c.faces_per_pixel = cfg.faces_per_pixel
+        c.cull_backfaces = int(cfg.cull_backfaces)
+        c.norm_with_object_size = int(cfg.norm_with_object_size)
+        c.tile_w, c.tile_h = cfg.tile_w, cfg.tile_h
+        c.blur_radius = cfg.blur_radius
+        c.sigma = cfg.sigma
+        c.proj_scale = cfg.proj_scale
+        c.z_clip = cfg.z_clip
+        c.step_size = cfg.step_size
+        for i in range(3):
+            c.light[i] = cfg.light[i]
+        c.done_threshold = cfg.done_threshold
+        c.reward_done = cfg.reward_done
+        c.reward_step = cfg.reward_step
+        L.check(self.lib.occl_config_resolve(ctypes.byref(c), 1), "occl_config_resolve")
+        self.c = c
+        self.c_scene = L.OcclScene(self.verts.data_ptr(), self.faces.data_ptr(), vstride, fstride)
+
+        N, S, dev = self.n, self.S, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        # per-env state (environment.py:302-306,323-324)
+        self.elevation = torch.zeros(N, **f32)
+        self.azimuth = torch.zeros(N, **f32)
+        self.radius = torch.full((N,), 4.0, **f32)
+        self.full_reward = torch.zeros(N, **f32)
+        self.object_mass = torch.ones(N, **f32)
+        self.c_state = L.OcclState(self.elevation.data_ptr(), self.azimuth.data_ptr(), self.radius.data_ptr(),
+                                   self.full_reward.data_ptr(), self.object_mass.data_ptr())
+        # outputs
+        self.obs = torch.empty(N, 4, S, S, **f32)
+        self.occl = torch.empty(N, S, S, **f32)
+        self.reward = torch.zeros(N, **f32)
+        self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.loss = torch.zeros(N, **f32)
+        self.position = torch.zeros(N, 3, **f32)
+        self.n_covered = torch.zeros(N, self.n_obj, dtype=torch.int32, device=dev)
+        self.n_visible = torch.zeros(N, self.n_obj, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.grad_action = torch.zeros(N, 2, **f32)
+        self.debug = debug_outputs
+        if debug_outputs:
+            self.alphas = torch.empty(N, self.n_obj, S, S, **f32)
+            self.pix_to_face = torch.empty(N, S, S, dtype=torch.int32, device=dev)
+            self.bary = torch.empty(N, S, S, 3, **f32)
+            self.nhits = torch.empty(N, self.n_obj, S, S, dtype=torch.int32, device=dev)
+        else:
+            self.alphas = self.pix_to_face = self.bary = self.nhits = None
+        nbytes = self.lib.occl_workspace_bytes(ctypes.byref(c), N, 1)
+        if nbytes == 0:
+            raise L.OcclError("occl_workspace_bytes returned 0 (invalid configuration)")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.c_ws = L.OcclWorkspace(self.workspace.data_ptr(), nbytes)
+
+    # ------------------------------------------------------------------------------------------
+    def outputs(self, with_grad: bool = False, obs: Optional[torch.Tensor] = None) -> L.OcclOutputs:
+        o = L.OcclOutputs()
+        o.obs = (self.obs if obs is None else obs).data_ptr()
+        o.occl = self.occl.data_ptr()
+        o.reward = self.reward.data_ptr()
+        o.done = self.done.data_ptr()
+        o.loss = self.loss.data_ptr()
+        o.position = self.position.data_ptr()
+        o.n_covered = self.n_covered.data_ptr()
+        o.n_visible = self.n_visible.data_ptr()
+        o.status = self.status.data_ptr()
+        o.grad_action = self.grad_action.data_ptr() if with_grad else None
+        if self.debug:
+            o.alphas = self.alphas.data_ptr()
+            o.pix_to_face = self.pix_to_face.data_ptr()
+            o.bary = self.bary.data_ptr()
+            o.nhits = self.nhits.data_ptr()
+        return o
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_pose(self, radius=None, azimuth=None, elevation=None):
+        for dst, src in ((self.radius, radius), (self.azimuth, azimuth), (self.elevation, elevation)):
+            if src is not None:
+                dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(self.device).expand_as(dst))
+
+    def reset(self, radius=None, azimuth=None, elevation=None, obs: Optional[torch.Tensor] = None):
+        """Render half of OcclusionEnv.reset (environment.py:302-328) for all envs."""
+        self.set_pose(radius, azimuth, elevation)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.occl_reset(ctypes.byref(self.c), self.n, self.c_scene, self.c_state, self.c_ws,
+                                        self.outputs(False, obs), self._stream()), "occl_reset")
+
+    def step(self, action: torch.Tensor, with_grad: bool = False, obs: Optional[torch.Tensor] = None):
+        """OcclusionEnv.step (environment.py:352-396) for all envs. action: (N,2) f32 on device."""
+        assert action.shape == (self.n, 2) and action.dtype == torch.float32 and action.is_cuda and action.is_contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.occl_step(ctypes.byref(self.c), self.n, _ptr(action), self.c_scene, self.c_state, self.c_ws,
+                                       self.outputs(with_grad, obs), self._stream()), "occl_step")
+
+    def render(self, R: torch.Tensor, T: torch.Tensor, C: torch.Tensor, obs: Optional[torch.Tensor] = None):
+        """Render from explicit cameras (environment.py:332-336); no state update."""
+        for t, shp in ((R, (self.n, 3, 3)), (T, (self.n, 3)), (C, (self.n, 3))):
+            assert tuple(t.shape) == shp and t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.occl_render(ctypes.byref(self.c), self.n, _ptr(R), _ptr(T), _ptr(C), self.c_scene, self.c_ws,
+                                         self.outputs(False, obs), self._stream()), "occl_render")
+
+    def camera_blocks(self) -> torch.Tensor:
+        """(N, 48) camera blocks of the last call (R, T, C and their tangents), for tests."""
+        n = self.n * L.OCCL_CAM_STRIDE * 4
+        return self.workspace[:n].view(torch.float32).view(self.n, L.OCCL_CAM_STRIDE).clone()
+
+    def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP):
+        st = int(torch.bitwise_or(self.status & raise_on, 0).max().item()) if self.n else 0
+        bad = int((self.status & raise_on).max().item())
+        if bad:
+            raise L.OcclError(f"env status flags set: {bad:#x} (1=z-clip needed, 4=hit buffer overflow, 8=overflow list full)")
+        return st

@@ -1,0 +1,305 @@
+"""CPU oracle for the OcclusionEnv transition -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu-baseline / ``--impl reference``
+legs may import this module.  The product package (``occlusionenv_b200``) never does.
+
+It wraps ``libocclusion_oracle.so`` (``occl_oracle.c``: the strict-fp32 restatement of the pytorch3d
+arithmetic) and restates the reference's state machine:
+
+  * constants            /root/reference/environment.py:234-284  (``createRenderers``)
+  * ``reset``            /root/reference/environment.py:286-328
+  * ``step``             /root/reference/environment.py:352-396
+  * vectorised loop      /root/reference/SubProcVecEnv.py:203-220 (sequential ``SimpleVecEnv``)
+
+PARITY UNPINNED: the reference has no tests or golden vectors and pytorch3d (its arithmetic) is not
+installable offline; see ``occl_oracle.c`` header and DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_f = ctypes.POINTER(ctypes.c_float)
+c_i = ctypes.POINTER(ctypes.c_int32)
+c_d = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libocclusion_oracle.so")
+    src = os.path.join(_HERE, "occl_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libocclusion_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+    return _LIB
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_f)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_i)
+
+
+# ------------------------------------------------------------------------------------------------
+# constants of createRenderers (environment.py:234-284), computed here independently of the product
+# ------------------------------------------------------------------------------------------------
+SIGMA = np.float32(1e-4)                                   # BlendParams(sigma=1e-4)      :242
+BLUR_RADIUS = np.float32(np.log(1.0 / 1e-4 - 1.0) * 1e-4)  # RasterizationSettings        :251
+FACES_PER_PIXEL = 100                                      #                              :252
+LIGHT = np.array([2.0, 2.0, -2.0], np.float32)             # PointLights location         :275
+STEP_SIZE = np.float32(0.05)                               #                              :219
+
+
+def fov_scale(fov_deg: float = 60.0, znear: float = 1.0) -> np.float32:
+    """K00 of FoVPerspectiveCameras (defaults fov=60 deg, znear=1), computed in fp32 like pytorch3d:
+    fov*(pi/180) -> tan(fov/2) -> max_y = tan*znear -> K00 = 2*znear/(max_x-min_x)."""
+    fov = np.float32(np.float32(fov_deg) * np.float32(np.pi / 180.0))
+    t = np.float32(np.tan(np.float32(fov / np.float32(2.0))))
+    max_y = np.float32(t * np.float32(znear))
+    return np.float32(np.float32(2.0 * znear) / np.float32(max_y - (-max_y)))
+
+
+PROJ_SCALE = fov_scale()
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers
+# ------------------------------------------------------------------------------------------------
+def pose_step(action, el, az, radius, step_size=STEP_SIZE):
+    """environment.py:356-368.  Returns (el', az', C(3), R(3,3), T(3)) in fp32."""
+    a = np.ascontiguousarray(action, np.float32)
+    e = ctypes.c_float(float(el))
+    z = ctypes.c_float(float(az))
+    C = np.zeros(3, np.float32)
+    R = np.zeros(9, np.float32)
+    T = np.zeros(3, np.float32)
+    lib().occl_oracle_pose_step(_fp(a), ctypes.c_float(float(step_size)), ctypes.c_float(float(radius)),
+                                ctypes.byref(e), ctypes.byref(z), _fp(C), _fp(R), _fp(T))
+    return np.float32(e.value), np.float32(z.value), C, R.reshape(3, 3), T
+
+
+def pose_lookat(radius, el, az):
+    """environment.py:308 (look_at_view_transform, radians)."""
+    C = np.zeros(3, np.float32)
+    R = np.zeros(9, np.float32)
+    T = np.zeros(3, np.float32)
+    lib().occl_oracle_pose_lookat(ctypes.c_float(float(radius)), ctypes.c_float(float(el)),
+                                  ctypes.c_float(float(az)), _fp(C), _fp(R), _fp(T))
+    return C, R.reshape(3, 3), T
+
+
+def look_at(C):
+    C = np.ascontiguousarray(C, np.float32)
+    R = np.zeros(9, np.float32)
+    T = np.zeros(3, np.float32)
+    lib().occl_oracle_look_at(_fp(C), _fp(R), _fp(T))
+    return R.reshape(3, 3), T
+
+
+def project(verts, R, T, s=PROJ_SCALE):
+    verts = np.ascontiguousarray(verts, np.float32)
+    R = np.ascontiguousarray(R, np.float32).reshape(-1)
+    T = np.ascontiguousarray(T, np.float32)
+    out = np.zeros_like(verts)
+    lib().occl_oracle_project(_fp(verts), verts.shape[0], _fp(R), _fp(T), ctypes.c_float(float(s)), _fp(out))
+    return out
+
+
+@dataclass
+class Fragments:
+    pix_to_face: np.ndarray  # (S,S,K) int32
+    zbuf: np.ndarray         # (S,S,K)
+    bary: np.ndarray         # (S,S,K,3)
+    dists: np.ndarray        # (S,S,K)
+    nhits: np.ndarray        # (S,S) hits before the K cut
+
+
+def rasterize(vproj, faces, S, blur_radius, K, cull_backfaces=True, perspective_correct=True,
+              clip_barycentric_coords=None) -> Fragments:
+    """MeshRasterizer.forward flags: clip_barycentric_coords defaults to blur>0."""
+    if clip_barycentric_coords is None:
+        clip_barycentric_coords = blur_radius > 0
+    vproj = np.ascontiguousarray(vproj, np.float32)
+    faces = np.ascontiguousarray(faces, np.int32)
+    p2f = np.empty((S, S, K), np.int32)
+    zb = np.empty((S, S, K), np.float32)
+    ba = np.empty((S, S, K, 3), np.float32)
+    di = np.empty((S, S, K), np.float32)
+    nh = np.zeros((S, S), np.int32)
+    lib().occl_oracle_rasterize(_fp(vproj), _ip(faces), faces.shape[0], S, ctypes.c_float(float(blur_radius)),
+                                K, int(perspective_correct), int(clip_barycentric_coords),
+                                int(cull_backfaces), _ip(p2f), _fp(zb), _fp(ba), _fp(di), _ip(nh))
+    return Fragments(p2f, zb, ba, di, nh)
+
+
+def silhouette(frag: Fragments, sigma=SIGMA) -> np.ndarray:
+    S, _, K = frag.pix_to_face.shape
+    alpha = np.empty((S, S), np.float32)
+    lib().occl_oracle_silhouette(_ip(frag.pix_to_face), _fp(frag.dists), S, K, ctypes.c_float(float(sigma)),
+                                 _fp(alpha))
+    return alpha
+
+
+def flat_shade(verts, faces, frag: Fragments, cam, light=LIGHT) -> np.ndarray:
+    """(4,S,S) observation: flat-shaded RGB + depth channel (environment.py:375-378)."""
+    S = frag.pix_to_face.shape[0]
+    verts = np.ascontiguousarray(verts, np.float32)
+    faces = np.ascontiguousarray(faces, np.int32)
+    obs = np.empty((4, S, S), np.float32)
+    p2f = np.ascontiguousarray(frag.pix_to_face[..., 0])
+    bary = np.ascontiguousarray(frag.bary[..., 0, :])
+    zb = np.ascontiguousarray(frag.zbuf[..., 0])
+    cam = np.ascontiguousarray(cam, np.float32)
+    light = np.ascontiguousarray(light, np.float32)
+    lib().occl_oracle_flat_shade(_fp(verts), _ip(faces), _ip(p2f), _fp(bary), _fp(zb), S, _fp(cam), _fp(light),
+                                 _fp(obs))
+    return obs
+
+
+def rasterize_backward(vproj, faces, frag: Fragments, grad_dists) -> np.ndarray:
+    vproj = np.ascontiguousarray(vproj, np.float32)
+    faces = np.ascontiguousarray(faces, np.int32)
+    S, _, K = frag.pix_to_face.shape
+    g = np.ascontiguousarray(grad_dists, np.float32)
+    out = np.zeros((vproj.shape[0], 3), np.float64)
+    lib().occl_oracle_rasterize_backward(_fp(vproj), _ip(faces), vproj.shape[0], S, K, 1,
+                                         _ip(frag.pix_to_face), _fp(g), out.ctypes.data_as(c_d))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# one render of the whole scene from (C, R, T): what reset() and step() share
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class RenderOut:
+    obs: np.ndarray            # (4,S,S)
+    alphas: np.ndarray         # (n_obj,S,S) soft silhouettes
+    occl: np.ndarray           # (S,S)  sum_{i<j} A_i A_j  (alpha channel of self.image)
+    loss: np.float32
+    objects_sq: np.float32     # sum (sum_i A_i)^2   (normWithObjectSize branch, :324)
+    pix_to_face: np.ndarray    # (S,S) scene K=1
+    zbuf: np.ndarray           # (S,S)
+    bary: np.ndarray           # (S,S,3)
+    nhits: np.ndarray          # (n_obj,S,S)
+    n_covered: np.ndarray      # (n_obj,) px hard-covered by object i rendered alone
+    n_visible: np.ndarray      # (n_obj,) px whose nearest scene face belongs to object i
+    vproj: np.ndarray          # (V,3)
+    frags: list                # per-object K=100 fragments (face ids local to the object)
+
+
+def render_scene(verts, faces, obj_face_start, obj_vert_start, S, C, R, T, s=PROJ_SCALE,
+                 blur=BLUR_RADIUS, sigma=SIGMA, K=FACES_PER_PIXEL, light=LIGHT) -> RenderOut:
+    n_obj = len(obj_face_start) - 1
+    vproj = project(verts, R, T, s)
+    alphas, nhits, n_cov, frags = [], [], [], []
+    for i in range(n_obj):
+        v0 = obj_vert_start[i]
+        f0, f1 = obj_face_start[i], obj_face_start[i + 1]
+        of = faces[f0:f1] - v0
+        ov = vproj[v0:obj_vert_start[i + 1]]
+        fr = rasterize(ov, of, S, blur, K)                       # silhouette settings :249-255
+        frags.append(fr)
+        alphas.append(silhouette(fr, sigma))
+        nhits.append(fr.nhits)
+        hard = rasterize(ov, of, S, 0.0, 1)                      # object alone, hard coverage
+        n_cov.append(int((hard.pix_to_face[..., 0] >= 0).sum()))
+    alphas = np.stack(alphas)
+    occl = np.zeros((S, S), np.float32)
+    for i in range(n_obj):
+        for j in range(i + 1, n_obj):
+            occl = occl + alphas[i] * alphas[j]                  # environment.py:373 generalised
+    loss = np.float32(np.sum((occl.astype(np.float64)) ** 2))
+    objs = np.sum(alphas.astype(np.float32), axis=0)
+    objects_sq = np.float32(np.sum(objs.astype(np.float64) ** 2))
+    scene = rasterize(vproj, faces, S, 0.0, 1)                   # observation settings :267-273
+    obs = flat_shade(verts, faces, scene, C, light)
+    p2f = scene.pix_to_face[..., 0]
+    n_vis = [int(((p2f >= obj_face_start[i]) & (p2f < obj_face_start[i + 1])).sum()) for i in range(n_obj)]
+    return RenderOut(obs, alphas, occl, loss, objects_sq, p2f, scene.zbuf[..., 0], scene.bary[..., 0, :],
+                     np.stack(nhits), np.asarray(n_cov), np.asarray(n_vis), vproj, frags)
+
+
+class OracleOcclusionEnv:
+    """Reference-faithful single environment (environment.py:201-402) on the CPU oracle.
+
+    Differences that are deliberate: n_obj-generic reward instead of the
+    hard-wired ``meshes[1..3]`` (B-1); no bare ``except`` retry loop; the scene is passed in.
+    """
+
+    def __init__(self, verts, faces, obj_face_start, obj_vert_start, img_size=512):
+        self.verts = np.ascontiguousarray(verts, np.float32)
+        self.faces = np.ascontiguousarray(faces, np.int32)
+        self.obj_face_start = np.asarray(obj_face_start, np.int32)
+        self.obj_vert_start = np.asarray(obj_vert_start, np.int32)
+        self.img_size = img_size
+        self.step_size = STEP_SIZE
+        self.normWithObjectSize = False
+        self.last = None
+
+    def _render(self, C, R, T):
+        self.last = render_scene(self.verts, self.faces, self.obj_face_start, self.obj_vert_start,
+                                 self.img_size, C, R, T)
+        return self.last
+
+    def reset(self, radius=4.0, azimuth=0.0, elevation=0.0):
+        self.camera_position = np.zeros(3, np.float32)            # :302
+        self.radius = np.float32(radius)
+        self.elevation = np.float32(elevation)
+        self.azimuth = np.float32(azimuth)
+        C, R, T = pose_lookat(self.radius, self.elevation, self.azimuth)  # :308
+        out = self._render(C, R, T)
+        self.fullReward = out.loss                                # :323
+        self.objectMass = np.float32((out.objects_sq if self.normWithObjectSize else out.loss) + np.float32(1))
+        return out.obs[None]
+
+    def step(self, action):
+        el, az, C, R, T = pose_step(action, self.elevation, self.azimuth, self.radius, self.step_size)
+        self.elevation, self.azimuth, self.camera_position = el, az, C
+        out = self._render(C, R, T)
+        loss = out.loss
+        reward = np.float32(self.fullReward - loss)               # :382
+        self.fullReward = loss                                    # :384
+        finished = bool(self.fullReward < np.float32(0.1))        # :386
+        reward = np.float32(reward / self.objectMass)             # :387
+        reward = np.float32(reward + np.float32(5)) if finished else np.float32(reward - np.float32(0.2))
+        info = {"full_state": out.occl, "position": C, "full_reward": self.fullReward}
+        return out.obs[None], reward, finished, info
+
+
+class OracleSimpleVecEnv:
+    """SubProcVecEnv.py:189-235: a sequential in-process loop (auto-reset with defaults on done)."""
+
+    def __init__(self, envs):
+        self.envs = envs
+        self.num_envs = len(envs)
+
+    def reset(self, azimuths=None):
+        return np.stack([e.reset(azimuth=0.0 if azimuths is None else azimuths[i]) for i, e in enumerate(self.envs)])
+
+    def step(self, actions):
+        obs, rews, dones, infos = [], [], [], []
+        for i, e in enumerate(self.envs):
+            o, r, d, info = e.step(actions[i])
+            if d:
+                info["terminal_observation"] = o
+                o = e.reset()
+            obs.append(o[0])
+            rews.append(r)
+            dones.append(d)
+            infos.append(info)
+        return np.stack(obs), np.asarray(rews, np.float32), np.asarray(dones), infos
