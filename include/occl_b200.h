@@ -120,6 +120,11 @@ int occl_config_resolve(OcclConfig* cfg, int with_grad);
 /* Scratch bytes for n_envs environments (camera blocks, projected vertices, tile partials). */
 size_t occl_workspace_bytes(const OcclConfig* cfg, int n_envs, int with_grad);
 
+/* Byte offsets inside the workspace of: camera blocks (N,OCCL_CAM_STRIDE) f32, projected vertices
+ * (N,V,4) f32, vertex tangents (N,V,4) f32 (with_grad only), tile partials.  For callers that drive
+ * the stages separately (occl_pose_* -> occl_project -> occl_raster -> occl_finalize). */
+int occl_workspace_offsets(const OcclConfig* cfg, int n_envs, int with_grad, size_t* offsets4);
+
 /* environment.py:356-368: normalise the action, integrate elevation/azimuth in place, camera centre
  * (step convention), look_at_rotation, T = -R^T C.  action (N,2) f32.  Writes the camera block
  * cam (N,OCCL_CAM_STRIDE): R[9] T[3] C[3] pad, then d/d_elevation and d/d_azimuth of the same. */
@@ -155,9 +160,12 @@ int occl_step(const OcclConfig* cfg, int n_envs, const float* action, OcclScene 
               OcclWorkspace ws, OcclOutputs out, void* stream);
 
 /* The render half of OcclusionEnv.reset (environment.py:302-328) for N environments whose
- * elevation/azimuth/radius have been written into `state` by the caller. */
-int occl_reset(const OcclConfig* cfg, int n_envs, OcclScene scene, OcclState state, OcclWorkspace ws,
-               OcclOutputs out, void* stream);
+ * elevation/azimuth/radius have been written into `state` by the caller.
+ * env_mask [opt] (N,) u8: only environments with a non-zero entry are reset, the others keep their
+ * state and outputs untouched -- the auto-reset of SimpleVecEnv.step_wait (SubProcVecEnv.py:211-214)
+ * without a host round trip (pass the `done` output of occl_step). */
+int occl_reset(const OcclConfig* cfg, int n_envs, const uint8_t* env_mask, OcclScene scene, OcclState state,
+               OcclWorkspace ws, OcclOutputs out, void* stream);
 
 /* Render from explicit cameras (environment.py:332-336 render(); parity tests): occl_pose_set ->
  * occl_project -> occl_raster.  No state update, no reward. */

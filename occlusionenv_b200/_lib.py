@@ -55,6 +55,7 @@ class OcclOutputs(Structure):
 
 # every symbol include/occl_b200.h declares
 EXPORTS = ["occl_abi_version", "occl_last_cuda_error", "occl_config_resolve", "occl_workspace_bytes",
+           "occl_workspace_offsets",
            "occl_pose_step", "occl_pose_lookat", "occl_pose_set", "occl_project", "occl_raster",
            "occl_finalize", "occl_step", "occl_reset", "occl_render"]
 
@@ -83,6 +84,8 @@ def load():
     lib.occl_config_resolve.restype = c_int
     lib.occl_workspace_bytes.argtypes = [P(OcclConfig), c_int, c_int]
     lib.occl_workspace_bytes.restype = c_size_t
+    lib.occl_workspace_offsets.argtypes = [P(OcclConfig), c_int, c_int, P(c_size_t)]
+    lib.occl_workspace_offsets.restype = c_int
     lib.occl_pose_step.argtypes = [P(OcclConfig), c_int, c_void_p, OcclState, c_void_p, c_void_p]
     lib.occl_pose_lookat.argtypes = [P(OcclConfig), c_int, OcclState, c_void_p, c_void_p]
     lib.occl_pose_set.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -90,7 +93,7 @@ def load():
     lib.occl_raster.argtypes = [P(OcclConfig), c_int, OcclScene, OcclWorkspace, OcclOutputs, c_void_p]
     lib.occl_finalize.argtypes = [P(OcclConfig), c_int, c_int, c_void_p, OcclState, OcclWorkspace, OcclOutputs, c_void_p]
     lib.occl_step.argtypes = [P(OcclConfig), c_int, c_void_p, OcclScene, OcclState, OcclWorkspace, OcclOutputs, c_void_p]
-    lib.occl_reset.argtypes = [P(OcclConfig), c_int, OcclScene, OcclState, OcclWorkspace, OcclOutputs, c_void_p]
+    lib.occl_reset.argtypes = [P(OcclConfig), c_int, c_void_p, OcclScene, OcclState, OcclWorkspace, OcclOutputs, c_void_p]
     lib.occl_render.argtypes = [P(OcclConfig), c_int, c_void_p, c_void_p, c_void_p, OcclScene, OcclWorkspace,
                                 OcclOutputs, c_void_p]
     for name in ("occl_pose_step", "occl_pose_lookat", "occl_pose_set", "occl_project", "occl_raster",

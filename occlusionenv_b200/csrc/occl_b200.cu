@@ -130,9 +130,11 @@ __device__ void look_at_store(const Dual C[3], float* __restrict__ cam) {
 __global__ void pose_kernel(int n, int mode, float step_size, const float* __restrict__ action,
                             float* __restrict__ el_p, float* __restrict__ az_p,
                             const float* __restrict__ radius_p, float* __restrict__ cam,
-                            float* __restrict__ position, uint32_t* __restrict__ status) {
+                            float* __restrict__ position, uint32_t* __restrict__ status,
+                            const uint8_t* __restrict__ env_mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (env_mask && !env_mask[e]) return;
   if (status) status[e] = 0u;
   float el = el_p[e], az = az_p[e];
   const float r = radius_p[e];
@@ -194,10 +196,11 @@ template <bool GRAD>
 __global__ void project_kernel(long long total, int V, const float* __restrict__ cam,
                                const float* __restrict__ verts, long long verts_stride, float s,
                                float z_clip, float4* __restrict__ vproj, float4* __restrict__ vtan,
-                               uint32_t* __restrict__ status) {
+                               uint32_t* __restrict__ status, const uint8_t* __restrict__ env_mask) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int e = (int)(idx / V);
+  if (env_mask && !env_mask[e]) return;
   const int v = (int)(idx - (long long)e * V);
   const float* __restrict__ c = cam + (size_t)e * OCCL_CAM_STRIDE;
   const float* __restrict__ p = verts + (size_t)e * verts_stride + (size_t)v * 3;
@@ -250,6 +253,7 @@ struct RasterParams {
   float* bary;
   int* nhits;
   uint32_t* status;
+  const uint8_t* env_mask;
 };
 
 struct FaceGeo {
@@ -510,6 +514,7 @@ raster_kernel(const RasterParams p) {
   const int n_tiles = p.tiles_x * p.tiles_y;
   const int env = blockIdx.x / n_tiles;
   const int tile = blockIdx.x - env * n_tiles;
+  if (p.env_mask && !p.env_mask[env]) return;
   const int tx0 = (tile % p.tiles_x) * p.tile_w;
   const int ty0 = (tile / p.tiles_x) * p.tile_h;
   const int tpx = p.tile_w * p.tile_h;
@@ -877,9 +882,11 @@ __global__ void finalize_kernel(int n, int mode, int n_tiles, int n_obj, int nor
                                 float* __restrict__ full_reward, float* __restrict__ object_mass,
                                 float* __restrict__ reward, uint8_t* __restrict__ done,
                                 float* __restrict__ loss_out, int* __restrict__ n_covered,
-                                int* __restrict__ n_visible, float* __restrict__ grad_action) {
+                                int* __restrict__ n_visible, float* __restrict__ grad_action,
+                                const uint8_t* __restrict__ env_mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
+  if (env_mask && !env_mask[e]) return;
   double loss = 0.0, objsq = 0.0, g0 = 0.0, g1 = 0.0;
   int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
   const Partial* __restrict__ pp = partials + (size_t)e * n_tiles;
@@ -1000,12 +1007,23 @@ extern "C" size_t occl_workspace_bytes(const OcclConfig* cfg, int n_envs, int wi
   return L.total;
 }
 
+extern "C" int occl_workspace_offsets(const OcclConfig* cfg, int n_envs, int with_grad, size_t* offsets4) {
+  if (!cfg || n_envs < 1 || !offsets4) return OCCL_E_INVALID;
+  OcclConfig c = *cfg;
+  int rc = occl_config_resolve(&c, with_grad);
+  if (rc != OCCL_OK) return rc;
+  WsLayout L;
+  ws_layout(&c, n_envs, with_grad, &L);
+  offsets4[0] = L.cam; offsets4[1] = L.vproj; offsets4[2] = L.vtan; offsets4[3] = L.partials;
+  return OCCL_OK;
+}
+
 static int launch_pose(const OcclConfig* c, int n, int mode, const float* action, OcclState st, float* cam,
-                       float* position, uint32_t* status, cudaStream_t s) {
+                       float* position, uint32_t* status, const uint8_t* mask, cudaStream_t s) {
   if (!st.elevation || !st.azimuth || !st.radius || !cam) return OCCL_E_INVALID;
   if (mode == 0 && !action) return OCCL_E_INVALID;
   pose_kernel<<<(n + 127) / 128, 128, 0, s>>>(n, mode, c->step_size, action, st.elevation, st.azimuth, st.radius,
-                                             cam, position, status);
+                                             cam, position, status, mask);
   CK(cudaGetLastError(), "pose_kernel");
   return OCCL_OK;
 }
@@ -1013,11 +1031,11 @@ static int launch_pose(const OcclConfig* c, int n, int mode, const float* action
 extern "C" int occl_pose_step(const OcclConfig* cfg, int n, const float* action, OcclState st, float* cam,
                               void* stream) {
   if (!cfg || n < 1) return OCCL_E_INVALID;
-  return launch_pose(cfg, n, 0, action, st, cam, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_pose(cfg, n, 0, action, st, cam, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 extern "C" int occl_pose_lookat(const OcclConfig* cfg, int n, OcclState st, float* cam, void* stream) {
   if (!cfg || n < 1) return OCCL_E_INVALID;
-  return launch_pose(cfg, n, 1, nullptr, st, cam, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_pose(cfg, n, 1, nullptr, st, cam, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 extern "C" int occl_pose_set(int n, const float* R, const float* T, const float* C, float* cam, void* stream) {
   if (n < 1 || !R || !T || !C || !cam) return OCCL_E_INVALID;
@@ -1026,21 +1044,26 @@ extern "C" int occl_pose_set(int n, const float* R, const float* T, const float*
   return OCCL_OK;
 }
 
-extern "C" int occl_project(const OcclConfig* cfg, int n, const float* cam, OcclScene sc, float* vproj, float* vtan,
-                            uint32_t* status, void* stream) {
+static int project_impl(const OcclConfig* cfg, int n, const float* cam, OcclScene sc, float* vproj, float* vtan,
+                        uint32_t* status, const uint8_t* mask, void* stream) {
   if (!cfg || n < 1 || !cam || !sc.verts || !vproj) return OCCL_E_INVALID;
   const long long total = (long long)n * cfg->n_verts;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   if (vtan)
     project_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(total, cfg->n_verts, cam, sc.verts, sc.verts_env_stride,
                                                                   cfg->proj_scale, cfg->z_clip, (float4*)vproj,
-                                                                  (float4*)vtan, status);
+                                                                  (float4*)vtan, status, mask);
   else
     project_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(total, cfg->n_verts, cam, sc.verts, sc.verts_env_stride,
                                                                    cfg->proj_scale, cfg->z_clip, (float4*)vproj, nullptr,
-                                                                   status);
+                                                                   status, mask);
   CK(cudaGetLastError(), "project_kernel");
   return OCCL_OK;
+}
+
+extern "C" int occl_project(const OcclConfig* cfg, int n, const float* cam, OcclScene sc, float* vproj, float* vtan,
+                            uint32_t* status, void* stream) {
+  return project_impl(cfg, n, cam, sc, vproj, vtan, status, nullptr, stream);
 }
 
 static int check_outputs(const OcclOutputs& o) {
@@ -1048,7 +1071,8 @@ static int check_outputs(const OcclOutputs& o) {
   return OCCL_OK;
 }
 
-extern "C" int occl_raster(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace ws, OcclOutputs out, void* stream) {
+static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace ws, OcclOutputs out, const uint8_t* mask,
+                       void* stream) {
   if (!cfg || n < 1 || !sc.verts || !sc.faces || !ws.base) return OCCL_E_INVALID;
   if (check_outputs(out) != OCCL_OK) return OCCL_E_INVALID;
   const int grad = out.grad_action != nullptr;
@@ -1075,7 +1099,7 @@ extern "C" int occl_raster(const OcclConfig* cfg, int n, OcclScene sc, OcclWorks
   p.cam = (const float*)(base + L.cam);
   p.partials = (Partial*)(base + L.partials);
   p.obs = out.obs; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
-  p.nhits = out.nhits; p.status = out.status;
+  p.nhits = out.nhits; p.status = out.status; p.env_mask = mask;
   const size_t smem = tile_smem_bytes(&c, grad);
   const long long blocks = (long long)n * L.n_tiles;
   if (blocks > 0x7fffffffLL) return OCCL_E_INVALID;
@@ -1090,8 +1114,12 @@ extern "C" int occl_raster(const OcclConfig* cfg, int n, OcclScene sc, OcclWorks
   return OCCL_OK;
 }
 
-extern "C" int occl_finalize(const OcclConfig* cfg, int n, int mode, const float* action, OcclState st, OcclWorkspace ws,
-                             OcclOutputs out, void* stream) {
+extern "C" int occl_raster(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace ws, OcclOutputs out, void* stream) {
+  return raster_impl(cfg, n, sc, ws, out, nullptr, stream);
+}
+
+static int finalize_impl(const OcclConfig* cfg, int n, int mode, const float* action, OcclState st, OcclWorkspace ws,
+                         OcclOutputs out, const uint8_t* mask, void* stream) {
   if (!cfg || n < 1 || !ws.base || mode < 0 || mode > 2) return OCCL_E_INVALID;
   const int grad = out.grad_action != nullptr;
   OcclConfig c = *cfg;
@@ -1107,13 +1135,19 @@ extern "C" int occl_finalize(const OcclConfig* cfg, int n, int mode, const float
   finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       n, mode, L.n_tiles, c.n_obj, c.norm_with_object_size, c.done_threshold, c.reward_done, c.reward_step, c.step_size,
       (const Partial*)(base + L.partials), action, st.full_reward, st.object_mass, out.reward, out.done, out.loss,
-      out.n_covered, out.n_visible, mode == 0 ? out.grad_action : nullptr);
+      out.n_covered, out.n_visible, mode == 0 ? out.grad_action : nullptr, mask);
   CK(cudaGetLastError(), "finalize_kernel");
   return OCCL_OK;
 }
 
+extern "C" int occl_finalize(const OcclConfig* cfg, int n, int mode, const float* action, OcclState st, OcclWorkspace ws,
+                             OcclOutputs out, void* stream) {
+  return finalize_impl(cfg, n, mode, action, st, ws, out, nullptr, stream);
+}
+
 static int run_chain(const OcclConfig* cfg, int n, int mode, const float* action, const float* R, const float* T,
-                     const float* C, OcclScene sc, OcclState st, OcclWorkspace ws, OcclOutputs out, void* stream) {
+                     const float* C, OcclScene sc, OcclState st, OcclWorkspace ws, OcclOutputs out, const uint8_t* mask,
+                     void* stream) {
   if (!cfg || n < 1 || !ws.base) return OCCL_E_INVALID;
   if (check_outputs(out) != OCCL_OK) return OCCL_E_INVALID;
   const int grad = out.grad_action != nullptr;
@@ -1130,26 +1164,27 @@ static int run_chain(const OcclConfig* cfg, int n, int mode, const float* action
     CK(cudaMemsetAsync(out.status, 0, sizeof(uint32_t) * (size_t)n, s), "memset status");
     rc = occl_pose_set(n, R, T, C, cam, stream);
   } else {
-    rc = launch_pose(&c, n, mode, action, st, cam, out.position, out.status, s);
+    rc = launch_pose(&c, n, mode, action, st, cam, out.position, out.status, mask, s);
   }
   if (rc != OCCL_OK) return rc;
-  rc = occl_project(&c, n, cam, sc, (float*)(base + L.vproj), grad ? (float*)(base + L.vtan) : nullptr, out.status, stream);
+  rc = project_impl(&c, n, cam, sc, (float*)(base + L.vproj), grad ? (float*)(base + L.vtan) : nullptr, out.status, mask,
+                    stream);
   if (rc != OCCL_OK) return rc;
-  rc = occl_raster(&c, n, sc, ws, out, stream);
+  rc = raster_impl(&c, n, sc, ws, out, mask, stream);
   if (rc != OCCL_OK) return rc;
-  return occl_finalize(&c, n, mode, action, st, ws, out, stream);
+  return finalize_impl(&c, n, mode, action, st, ws, out, mask, stream);
 }
 
 extern "C" int occl_step(const OcclConfig* cfg, int n, const float* action, OcclScene sc, OcclState st, OcclWorkspace ws,
                          OcclOutputs out, void* stream) {
   if (!action) return OCCL_E_INVALID;
-  return run_chain(cfg, n, 0, action, nullptr, nullptr, nullptr, sc, st, ws, out, stream);
+  return run_chain(cfg, n, 0, action, nullptr, nullptr, nullptr, sc, st, ws, out, nullptr, stream);
 }
-extern "C" int occl_reset(const OcclConfig* cfg, int n, OcclScene sc, OcclState st, OcclWorkspace ws, OcclOutputs out,
-                          void* stream) {
+extern "C" int occl_reset(const OcclConfig* cfg, int n, const uint8_t* env_mask, OcclScene sc, OcclState st,
+                          OcclWorkspace ws, OcclOutputs out, void* stream) {
   OcclOutputs o = out;
   o.grad_action = nullptr;
-  return run_chain(cfg, n, 1, nullptr, nullptr, nullptr, nullptr, sc, st, ws, o, stream);
+  return run_chain(cfg, n, 1, nullptr, nullptr, nullptr, nullptr, sc, st, ws, o, env_mask, stream);
 }
 extern "C" int occl_render(const OcclConfig* cfg, int n, const float* R, const float* T, const float* C, OcclScene sc,
                            OcclWorkspace ws, OcclOutputs out, void* stream) {
@@ -1157,5 +1192,5 @@ extern "C" int occl_render(const OcclConfig* cfg, int n, const float* R, const f
   OcclOutputs o = out;
   o.grad_action = nullptr;
   OcclState st = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  return run_chain(cfg, n, 2, nullptr, R, T, C, sc, st, ws, o, stream);
+  return run_chain(cfg, n, 2, nullptr, R, T, C, sc, st, ws, o, nullptr, stream);
 }

@@ -111,9 +111,21 @@ class OcclusionEngine:
         self.c_ws = L.OcclWorkspace(self.workspace.data_ptr(), nbytes)
 
     # ------------------------------------------------------------------------------------------
-    def outputs(self, with_grad: bool = False, obs: Optional[torch.Tensor] = None) -> L.OcclOutputs:
+    def outputs(self, with_grad: bool = False, obs: Optional[torch.Tensor] = None, scratch: bool = False) -> L.OcclOutputs:
+        """Device pointers of the output buffers.  ``scratch=True`` routes everything except ``obs``
+        and ``status`` into throw-away buffers (used by ``render()`` so that the results of the last
+        transition stay intact)."""
         o = L.OcclOutputs()
         o.obs = (self.obs if obs is None else obs).data_ptr()
+        if scratch:
+            if getattr(self, "_scratch", None) is None:
+                self._scratch = dict(occl=torch.empty_like(self.occl), loss=torch.empty_like(self.loss),
+                                     ncov=torch.empty_like(self.n_covered), nvis=torch.empty_like(self.n_visible))
+            sc = self._scratch
+            o.occl, o.loss = sc["occl"].data_ptr(), sc["loss"].data_ptr()
+            o.n_covered, o.n_visible = sc["ncov"].data_ptr(), sc["nvis"].data_ptr()
+            o.status = self.status.data_ptr()
+            return o
         o.occl = self.occl.data_ptr()
         o.reward = self.reward.data_ptr()
         o.done = self.done.data_ptr()
@@ -138,11 +150,22 @@ class OcclusionEngine:
             if src is not None:
                 dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(self.device).expand_as(dst))
 
-    def reset(self, radius=None, azimuth=None, elevation=None, obs: Optional[torch.Tensor] = None):
-        """Render half of OcclusionEnv.reset (environment.py:302-328) for all envs."""
-        self.set_pose(radius, azimuth, elevation)
+    def reset(self, radius=None, azimuth=None, elevation=None, obs: Optional[torch.Tensor] = None,
+              mask: Optional[torch.Tensor] = None):
+        """Render half of OcclusionEnv.reset (environment.py:302-328).  ``mask`` (N,) uint8/bool on the
+        device restricts the reset (pose values included) to the flagged envs."""
+        if mask is not None:
+            mask = mask.to(torch.uint8)
+            assert mask.shape == (self.n,) and mask.is_cuda and mask.is_contiguous()
+            mb = mask.bool()
+            for dst, src in ((self.radius, radius), (self.azimuth, azimuth), (self.elevation, elevation)):
+                if src is not None:
+                    v = torch.as_tensor(src, dtype=torch.float32).to(self.device).expand_as(dst)
+                    dst.copy_(torch.where(mb, v, dst))
+        else:
+            self.set_pose(radius, azimuth, elevation)
         with torch.cuda.device(self.device):
-            L.check(self.lib.occl_reset(ctypes.byref(self.c), self.n, self.c_scene, self.c_state, self.c_ws,
+            L.check(self.lib.occl_reset(ctypes.byref(self.c), self.n, _ptr(mask), self.c_scene, self.c_state, self.c_ws,
                                         self.outputs(False, obs), self._stream()), "occl_reset")
 
     def step(self, action: torch.Tensor, with_grad: bool = False, obs: Optional[torch.Tensor] = None):
@@ -152,22 +175,48 @@ class OcclusionEngine:
             L.check(self.lib.occl_step(ctypes.byref(self.c), self.n, _ptr(action), self.c_scene, self.c_state, self.c_ws,
                                        self.outputs(with_grad, obs), self._stream()), "occl_step")
 
-    def render(self, R: torch.Tensor, T: torch.Tensor, C: torch.Tensor, obs: Optional[torch.Tensor] = None):
+    def render(self, R: torch.Tensor, T: torch.Tensor, C: torch.Tensor, obs: Optional[torch.Tensor] = None,
+               scratch: bool = False):
         """Render from explicit cameras (environment.py:332-336); no state update."""
         for t, shp in ((R, (self.n, 3, 3)), (T, (self.n, 3)), (C, (self.n, 3))):
             assert tuple(t.shape) == shp and t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
         with torch.cuda.device(self.device):
             L.check(self.lib.occl_render(ctypes.byref(self.c), self.n, _ptr(R), _ptr(T), _ptr(C), self.c_scene, self.c_ws,
-                                         self.outputs(False, obs), self._stream()), "occl_render")
+                                         self.outputs(False, obs, scratch), self._stream()), "occl_render")
+
+    def step_staged(self, action: torch.Tensor, with_grad: bool = False, raster_events=None):
+        """The same transition as ``step`` driven stage by stage through the split C-ABI entry points
+        (occl_pose_step -> occl_project -> occl_raster -> occl_finalize).  ``raster_events`` = (start,
+        end) CUDA events recorded around the rasteriser launch (bench.py's roofline timing)."""
+        lib, c, n = self.lib, ctypes.byref(self.c), self.n
+        offs = (ctypes.c_size_t * 4)()
+        L.check(lib.occl_workspace_offsets(c, n, int(with_grad), offs), "occl_workspace_offsets")
+        base = self.workspace.data_ptr()
+        cam, vproj = ctypes.c_void_p(base + offs[0]), ctypes.c_void_p(base + offs[1])
+        vtan = ctypes.c_void_p(base + offs[2]) if with_grad else None
+        st = self._stream()
+        out = self.outputs(with_grad)
+        with torch.cuda.device(self.device):
+            self.status.zero_()
+            L.check(lib.occl_pose_step(c, n, _ptr(action), self.c_state, cam, st), "occl_pose_step")
+            L.check(lib.occl_project(c, n, cam, self.c_scene, vproj, vtan, _ptr(self.status), st), "occl_project")
+            if raster_events is not None:
+                raster_events[0].record()
+            L.check(lib.occl_raster(c, n, self.c_scene, self.c_ws, out, st), "occl_raster")
+            if raster_events is not None:
+                raster_events[1].record()
+            L.check(lib.occl_finalize(c, n, 0, _ptr(action), self.c_state, self.c_ws, out, st), "occl_finalize")
 
     def camera_blocks(self) -> torch.Tensor:
         """(N, 48) camera blocks of the last call (R, T, C and their tangents), for tests."""
         n = self.n * L.OCCL_CAM_STRIDE * 4
         return self.workspace[:n].view(torch.float32).view(self.n, L.OCCL_CAM_STRIDE).clone()
 
-    def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP):
-        st = int(torch.bitwise_or(self.status & raise_on, 0).max().item()) if self.n else 0
+    def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP) -> int:
+        """Host-syncing check of the per-env status words; raises on conditions the kernels flag
+        instead of computing (z-clip needed, selection buffers exceeded)."""
         bad = int((self.status & raise_on).max().item())
         if bad:
-            raise L.OcclError(f"env status flags set: {bad:#x} (1=z-clip needed, 4=hit buffer overflow, 8=overflow list full)")
-        return st
+            raise L.OcclError(f"env status flags set: {bad:#x} (1=z-clip needed, 4=hit buffer overflow, "
+                              "8=overflow list full)")
+        return int(self.status.max().item())

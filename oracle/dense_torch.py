@@ -1,0 +1,188 @@
+"""Oracle (b): dense PyTorch formulation of the same transition -- TEST INFRASTRUCTURE ONLY.
+
+Written independently of ``occl_oracle.c`` (broadcast pixel x face tensors instead of scalar loops) from
+SURVEY.md Appendix A, for two purposes:
+  1. cross-check the C restatement (forward values), and
+  2. provide the gradient oracle: d reward / d action by autograd through pose -> projection ->
+     point/triangle distances -> sigmoid blend -> occlusion loss (the route of ``demo.py:85-86``),
+     in float64 so that it can also be validated against finite differences.
+
+Reference lines restated: ``environment.py:356-368`` (pose), ``:373,381-392`` (reward) and the pytorch3d
+pieces listed in ``occl_oracle.c``.  PARITY UNPINNED (no pytorch3d offline), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+K_EPS = 1e-8
+
+
+def _normalize(v, eps):
+    return v / v.norm().clamp_min(eps)
+
+
+def look_at(C):
+    up = torch.tensor([0.0, 1.0, 0.0], dtype=C.dtype)
+    z = _normalize(-C, 1e-5)
+    x = _normalize(torch.linalg.cross(up, z), 1e-5)
+    y = _normalize(torch.linalg.cross(z, x), 1e-5)
+    if bool((x.abs() <= 5e-3).all()):
+        x = _normalize(torch.linalg.cross(y, z), 1e-5)
+    R = torch.stack([x, y, z], dim=1)
+    T = -(R.t() @ C)
+    return R, T
+
+
+def pose_step(action, el, az, radius, step_size=0.05):
+    n = action.norm()
+    na = action / n if float(n.detach()) != 0.0 else action
+    el = el + na[0] * step_size
+    az = az + na[1] * step_size
+    C = torch.stack([radius * torch.sin(az) * torch.cos(el), radius * torch.sin(az) * torch.sin(el),
+                     radius * torch.cos(az)])
+    R, T = look_at(C)
+    return el, az, C, R, T
+
+
+def pose_lookat(radius, el, az):
+    C = torch.stack([radius * torch.cos(el) * torch.sin(az), radius * torch.sin(el),
+                     radius * torch.cos(el) * torch.cos(az)])
+    R, T = look_at(C)
+    return C, R, T
+
+
+def project(verts, R, T, s):
+    vv = verts @ R + T
+    return torch.stack([s * vv[:, 0] / vv[:, 2], s * vv[:, 1] / vv[:, 2], vv[:, 2]], dim=1)
+
+
+def _edge(px, py, ax, ay, bx, by):
+    return (px - ax) * (by - ay) - (py - ay) * (bx - ax)
+
+
+def _seg(px, py, ax, ay, bx, by):
+    bax, bay = bx - ax, by - ay
+    l2 = bax * bax + bay * bay
+    degenerate = l2 <= K_EPS
+    t = (bax * (px - ax) + bay * (py - ay)) / torch.where(degenerate, torch.ones_like(l2), l2)
+    t = t.clamp(0.0, 1.0)
+    t = torch.where(degenerate, torch.ones_like(t), t)
+    qx, qy = ax + t * bax, ay + t * bay
+    return (px - qx) ** 2 + (py - qy) ** 2
+
+
+def pixel_centers(S, dtype):
+    i = torch.arange(S, dtype=dtype)
+    c = -1.0 + (2.0 * (S - 1 - i) + 1.0) / S  # centre of output index i (rows and columns alike)
+    return c
+
+
+def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
+    """Soft silhouette alpha for the pixel rows ``rows`` (1-D long tensor): (len(rows), S)."""
+    dtype = vproj.dtype
+    fv = vproj[faces]  # (F,3,3)
+    x0, y0, z0 = fv[:, 0, 0], fv[:, 0, 1], fv[:, 0, 2]
+    x1, y1, z1 = fv[:, 1, 0], fv[:, 1, 1], fv[:, 1, 2]
+    x2, y2, z2 = fv[:, 2, 0], fv[:, 2, 1], fv[:, 2, 2]
+    face_area = _edge(x0, y0, x1, y1, x2, y2)
+    zmin = torch.minimum(torch.minimum(z0, z1), z2)
+    valid = (face_area.abs() > K_EPS) & ~(zmin < K_EPS)
+    if cull:
+        valid &= ~(face_area < 0)
+    r = math.sqrt(blur)
+    xmin = torch.minimum(torch.minimum(x0, x1), x2) - r
+    xmax = torch.maximum(torch.maximum(x0, x1), x2) + r
+    ymin = torch.minimum(torch.minimum(y0, y1), y2) - r
+    ymax = torch.maximum(torch.maximum(y0, y1), y2) + r
+    c = pixel_centers(S, dtype)
+    py = c[rows]
+    # drop faces that cannot touch these rows (pure speed-up, no semantic effect)
+    keep = valid & (ymax.detach() >= py.min()) & (ymin.detach() <= py.max())
+    idx = keep.nonzero()[:, 0]
+    if idx.numel() == 0:
+        return torch.zeros(len(rows), S, dtype=dtype)
+    sel = lambda a: a[idx][None, :]  # noqa: E731
+    x0, y0, z0, x1, y1, z1, x2, y2, z2 = map(sel, (x0, y0, z0, x1, y1, z1, x2, y2, z2))
+    xmin, xmax, ymin, ymax = map(sel, (xmin, xmax, ymin, ymax))
+    PX = c[None, :].expand(len(rows), S).reshape(-1, 1)
+    PY = py[:, None].expand(len(rows), S).reshape(-1, 1)
+    in_box = ~((PX > xmax) | (PX < xmin) | (PY > ymax) | (PY < ymin))
+    area = _edge(x2, y2, x0, y0, x1, y1) + K_EPS
+    w0 = _edge(PX, PY, x1, y1, x2, y2) / area
+    w1 = _edge(PX, PY, x2, y2, x0, y0) / area
+    w2 = _edge(PX, PY, x0, y0, x1, y1) / area
+    t0, t1, t2 = w0 * z1 * z2, z0 * w1 * z2, z0 * z1 * w2
+    den = (t0 + t1 + t2).clamp_min(K_EPS)
+    b0, b1, b2 = t0 / den, t1 / den, t2 / den
+    inside = (b0 > 0) & (b1 > 0) & (b2 > 0)
+    c0, c1, c2 = b0.clamp_min(0), b1.clamp_min(0), b2.clamp_min(0)
+    sm = (c0 + c1 + c2).clamp_min(1e-5)
+    pz = (c0 * z0 + c1 * z1 + c2 * z2) / sm
+    dist = torch.minimum(torch.minimum(_seg(PX, PY, x0, y0, x1, y1), _seg(PX, PY, x0, y0, x2, y2)),
+                         _seg(PX, PY, x1, y1, x2, y2))
+    hit = in_box & (pz >= 0) & (inside | (dist < blur))
+    nh = hit.sum(dim=1)
+    if int(nh.max()) > K:
+        # keep the K nearest by (pz, face index): stable sort on pz keeps the lower index first on ties
+        key = torch.where(hit, pz.detach(), torch.full_like(pz, float("inf")))
+        order = torch.sort(key, dim=1, stable=True).indices
+        rank = torch.empty_like(order)
+        rank.scatter_(1, order, torch.arange(order.shape[1]).expand_as(order))
+        hit = hit & (rank < K)
+    sd = torch.where(inside, -dist, dist)
+    prob = torch.sigmoid(-sd / sigma) * hit.to(dtype)
+    alpha = 1.0 - torch.prod(1.0 - prob, dim=1)
+    return alpha.reshape(len(rows), S)
+
+
+def occlusion_loss(verts, faces, obj_face_start, obj_vert_start, S, R, T, s, blur, sigma, K, row_chunk=16,
+                   backward=False):
+    """loss = sum_px (sum_{i<j} A_i A_j)^2 (``environment.py:373,381``), evaluated in row chunks.  With
+    ``backward=True`` every chunk is back-propagated immediately (the graph of one chunk is alive at a
+    time) and the float value is returned; otherwise a differentiable tensor is returned."""
+    n_obj = len(obj_face_start) - 1
+    total = torch.zeros((), dtype=verts.dtype)
+    total_val = 0.0
+    alphas = []
+    for r0 in range(0, S, row_chunk):
+        rows = torch.arange(r0, min(S, r0 + row_chunk))
+        vproj = project(verts, R, T, s)
+        A = []
+        for i in range(n_obj):
+            v0, v1 = int(obj_vert_start[i]), int(obj_vert_start[i + 1])
+            f0, f1 = int(obj_face_start[i]), int(obj_face_start[i + 1])
+            A.append(soft_alpha_rows(vproj[v0:v1], faces[f0:f1] - v0, S, rows, blur, sigma, K))
+        occl = torch.zeros_like(A[0])
+        for i in range(n_obj):
+            for j in range(i + 1, n_obj):
+                occl = occl + A[i] * A[j]
+        part = (occl ** 2).sum()
+        alphas.append(torch.stack([a.detach() for a in A]))
+        if backward:
+            if part.requires_grad:
+                part.backward(retain_graph=True)
+            total_val += float(part.detach())
+        else:
+            total = total + part
+    alphas = torch.cat(alphas, dim=1)
+    return (total_val if backward else total), alphas
+
+
+def reward_and_grad(scene, S, action, el0, az0, radius, prev_loss, mass, s, blur, sigma, K=100, step_size=0.05,
+                    dtype=torch.float64):
+    """d reward / d action for one env by autograd (``environment.py:352-392`` in one differentiable
+    graph).  Returns (reward, loss, grad_action (2,), alphas)."""
+    verts = torch.tensor(scene.verts, dtype=dtype)
+    faces = torch.tensor(scene.faces, dtype=torch.long)
+    a = torch.tensor(np.asarray(action), dtype=dtype, requires_grad=True)
+    el, az, C, R, T = pose_step(a, torch.tensor(float(el0), dtype=dtype), torch.tensor(float(az0), dtype=dtype),
+                                torch.tensor(float(radius), dtype=dtype), step_size)
+    loss_val, alphas = occlusion_loss(verts, faces, scene.obj_face_start, scene.obj_vert_start, S, R, T, s, blur,
+                                      sigma, K, backward=True)
+    # reward = (prev - loss)/mass + const  ->  d reward / d a = -(d loss / d a) / mass
+    g = a.grad if a.grad is not None else torch.zeros_like(a)
+    reward = (prev_loss - loss_val) / mass
+    return reward, loss_val, (-g / mass).numpy(), alphas.numpy()

@@ -12,6 +12,9 @@ from occlusionenv_b200.meshes import default_scene
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5  # north-star tolerance for silhouettes / depth / reward
+# alpha = 1 - prod(1 - p) is formed in fp32: its absolute resolution is the ulp of 1.0 (1.2e-7) per
+# multiply, whatever the size of alpha; allow 4 ulp(1.0) absolute on top of the relative bound.
+ATOL_A = 5e-7
 
 
 def _poses(oracle, kind):
@@ -57,8 +60,8 @@ def test_render_matches_oracle(oracle, cuda_lib, occluder, S):
         assert np.array_equal(obs[3], ref.obs[3]), "depth channel must be bit-identical (same fp32 ops)"
         np.testing.assert_allclose(obs[:3], ref.obs[:3], rtol=RTOL, atol=1e-6)
         np.testing.assert_allclose(eng.bary[e].cpu().numpy(), ref.bary, rtol=0, atol=0)
-        np.testing.assert_allclose(eng.alphas[e].cpu().numpy(), ref.alphas, rtol=RTOL, atol=1e-7)
-        np.testing.assert_allclose(eng.occl[e].cpu().numpy(), ref.occl, rtol=2 * RTOL, atol=1e-7)
+        np.testing.assert_allclose(eng.alphas[e].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
+        np.testing.assert_allclose(eng.occl[e].cpu().numpy(), ref.occl, rtol=2 * RTOL, atol=2 * ATOL_A)
         np.testing.assert_allclose(float(eng.loss[e]), float(ref.loss), rtol=RTOL, atol=1e-6)
         if (ref.nhits > 100).any():
             assert status[e] & 2

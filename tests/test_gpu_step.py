@@ -1,0 +1,264 @@
+"""GPU parity of the whole transition (reset + step, reward/done/state, gradient, golden fixtures) and of
+the reference-facing API (OcclusionEnv, BatchedOcclusionVecEnv, SimpleVecEnv)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from occlusionenv_b200.config import RasterConfig
+from occlusionenv_b200.meshes import default_scene, procedural_scene
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-5
+ATOL_A = 5e-7  # 4 ulp of 1.0: alpha = 1 - prod(1-p) in fp32 (see test_gpu_render_parity.py)
+
+
+def _engine(sc, n, S, **kw):
+    from occlusionenv_b200.engine import OcclusionEngine
+    return OcclusionEngine(sc, n, RasterConfig(image_size=S), **kw)
+
+
+def test_pose_kernels_bit_identical_to_oracle(oracle, cuda_lib):
+    sc = default_scene("box")
+    rng = np.random.default_rng(0)
+    n = 257
+    az = rng.uniform(-3, 3, n).astype(np.float32)
+    el = rng.uniform(-1.2, 1.2, n).astype(np.float32)
+    act = rng.normal(size=(n, 2)).astype(np.float32)
+    act[3] = 0.0
+    eng = _engine(sc, n, 16)
+    eng.set_pose(4.0, torch.tensor(az), torch.tensor(el))
+    from occlusionenv_b200 import _lib as L
+    import ctypes
+    cam = torch.zeros(n, L.OCCL_CAM_STRIDE, device="cuda")
+    L.check(cuda_lib.occl_pose_lookat(ctypes.byref(eng.c), n, eng.c_state, cam.data_ptr(), None), "lookat")
+    cam_l = cam.cpu().numpy()
+    L.check(cuda_lib.occl_pose_step(ctypes.byref(eng.c), n, torch.tensor(act, device="cuda").data_ptr(), eng.c_state,
+                                    cam.data_ptr(), None), "step")
+    cam_s = cam.cpu().numpy()
+    el2, az2 = eng.elevation.cpu().numpy(), eng.azimuth.cpu().numpy()
+    for e in range(n):
+        C, R, T = oracle.pose_lookat(4.0, el[e], az[e])
+        assert np.array_equal(cam_l[e, :9].reshape(3, 3), R) and np.array_equal(cam_l[e, 9:12], T) and np.array_equal(cam_l[e, 12:15], C)
+        oe, oa, C, R, T = oracle.pose_step(act[e], el[e], az[e], 4.0)
+        assert oe == el2[e] and oa == az2[e]
+        assert np.array_equal(cam_s[e, :9].reshape(3, 3), R) and np.array_equal(cam_s[e, 9:12], T) and np.array_equal(cam_s[e, 12:15], C)
+
+
+@pytest.mark.parametrize("occ", ["teapot", "box"])
+def test_golden_fixtures(cuda_lib, occ):
+    g = np.load(os.path.join(GOLD, f"scene_{occ}_128.npz"))
+    sc = default_scene(occ)
+    n = len(g["poses"])
+    eng = _engine(sc, n, 128, debug_outputs=True)
+    R = torch.tensor(np.stack([g[f"R{k}"] for k in range(n)]), device="cuda").contiguous()
+    T = torch.tensor(np.stack([g[f"T{k}"] for k in range(n)]), device="cuda").contiguous()
+    C = torch.tensor(np.stack([g[f"C{k}"] for k in range(n)]), device="cuda").contiguous()
+    eng.render(R, T, C)
+    eng.check_status()
+    for k in range(n):
+        assert np.array_equal(eng.pix_to_face[k].cpu().numpy().astype(np.int16), g[f"pix_to_face{k}"])
+        assert np.array_equal(eng.obs[k, 3].cpu().numpy(), g[f"zbuf{k}"])
+        assert np.array_equal(eng.n_covered[k].cpu().numpy(), g[f"n_covered{k}"])
+        assert np.array_equal(eng.n_visible[k].cpu().numpy(), g[f"n_visible{k}"])
+        assert int(eng.nhits[k].max()) == int(g[f"nhits_max{k}"])
+        np.testing.assert_allclose(eng.alphas[k].cpu().numpy(), g[f"alphas{k}"], rtol=RTOL, atol=ATOL_A)
+        np.testing.assert_allclose(eng.obs[k, 0].cpu().numpy(), g[f"rgb{k}"], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(float(eng.loss[k]), float(g[f"loss{k}"]), rtol=RTOL, atol=1e-6)
+
+
+def test_trajectory_matches_oracle_state_machine(oracle, cuda_lib):
+    """reset + several steps for a batch of envs: reward / done / loss / state, every step."""
+    sc = default_scene("teapot")
+    S, n, steps = 64, 6, 3
+    rng = np.random.default_rng(1)
+    az0 = rng.uniform(np.pi / 2 - 0.6, np.pi / 2 + 0.6, n).astype(np.float32)
+    az0[0] = 0.0  # no occlusion -> done on the first step
+    el0 = rng.uniform(-0.3, 0.3, n).astype(np.float32)
+    acts = rng.normal(size=(steps, n, 2)).astype(np.float32)
+    acts[1, 2] = 0.0
+    eng = _engine(sc, n, S, debug_outputs=True)
+    eng.reset(radius=4.0, azimuth=torch.tensor(az0), elevation=torch.tensor(el0))
+    refs = []
+    for e in range(n):
+        r = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S)
+        obs = r.reset(radius=4.0, azimuth=az0[e], elevation=el0[e])
+        np.testing.assert_allclose(eng.obs[e].cpu().numpy(), obs[0], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(float(eng.full_reward[e]), float(r.fullReward), rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(float(eng.object_mass[e]), float(r.objectMass), rtol=RTOL)
+        refs.append(r)
+    for t in range(steps):
+        eng.step(torch.tensor(acts[t], device="cuda"))
+        eng.check_status()
+        for e, r in enumerate(refs):
+            obs, rew, done, info = r.step(acts[t, e])
+            assert np.array_equal(eng.pix_to_face[e].cpu().numpy(), r.last.pix_to_face)
+            assert np.array_equal(eng.n_visible[e].cpu().numpy(), r.last.n_visible)
+            np.testing.assert_allclose(eng.obs[e].cpu().numpy(), obs[0], rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(eng.occl[e].cpu().numpy(), info["full_state"], rtol=2 * RTOL, atol=2 * ATOL_A)
+            np.testing.assert_allclose(float(eng.reward[e]), float(rew), rtol=RTOL, atol=2e-6)
+            np.testing.assert_allclose(float(eng.loss[e]), float(info["full_reward"]), rtol=RTOL, atol=1e-6)
+            assert bool(eng.done[e]) == bool(done)
+            np.testing.assert_array_equal(eng.position[e].cpu().numpy(), info["position"])
+            assert float(eng.elevation[e]) == float(r.elevation) and float(eng.azimuth[e]) == float(r.azimuth)
+    assert bool(eng.done[0])
+
+
+@pytest.mark.parametrize("occ", ["teapot", "box"])
+def test_gradient_to_action_matches_dense_autograd(oracle, cuda_lib, occ):
+    """north-star tolerance: pose gradients within 1e-3 relative (vs float64 autograd of oracle (b))."""
+    from oracle import dense_torch as D
+    sc = default_scene(occ)
+    S = 64
+    cases = [(1.45, 0.1, (0.3, -1.0)), (1.7, -0.2, (-0.5, 0.2)), (1.3, 0.25, (1.0, 1.0)), (1.55, 0.0, (0.0, 0.0))]
+    n = len(cases)
+    eng = _engine(sc, n, S)
+    az0 = np.array([c[0] for c in cases], np.float32)
+    el0 = np.array([c[1] for c in cases], np.float32)
+    eng.reset(radius=4.0, azimuth=torch.tensor(az0), elevation=torch.tensor(el0))
+    prev = eng.full_reward.cpu().numpy().copy()
+    mass = eng.object_mass.cpu().numpy().copy()
+    act = np.array([c[2] for c in cases], np.float32)
+    eng.step(torch.tensor(act, device="cuda"), with_grad=True)
+    eng.check_status()
+    g_gpu = eng.grad_action.cpu().numpy()
+    for e in range(n):
+        r, loss, g, _ = D.reward_and_grad(sc, S, act[e].astype(np.float64), el0[e], az0[e], 4.0, float(prev[e]), float(mass[e]),
+                                          float(oracle.PROJ_SCALE), float(oracle.BLUR_RADIUS), float(oracle.SIGMA))
+        np.testing.assert_allclose(float(eng.loss[e]), loss, rtol=1e-5)
+        scale = max(np.abs(g).max(), 1e-6)
+        assert np.abs(g_gpu[e] - g).max() <= 1e-3 * scale, (e, g_gpu[e], g)
+    # the non-differentiable forward gives the same reward
+    eng2 = _engine(sc, n, S)
+    eng2.reset(radius=4.0, azimuth=torch.tensor(az0), elevation=torch.tensor(el0))
+    eng2.step(torch.tensor(act, device="cuda"), with_grad=False)
+    np.testing.assert_allclose(eng2.reward.cpu().numpy(), eng.reward.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_occlusion_env_dropin_contract(oracle, cuda_lib):
+    """Shapes / dtypes / attributes of environment.py:201-402 and autograd through reward (demo.py:85-91)."""
+    from occlusionenv_b200.environment import OcclusionEnv
+    S = 64
+    env = OcclusionEnv(img_size=S)
+    assert env.observation_space.shape == (4, S, S) and env.action_space.shape == (2,)
+    assert env.step_size == 0.05 and env.normWithObjectSize is False and env.renderMode == ""
+    env.seed(3)
+    obs = env.reset(azimuth=1.5)
+    assert obs.shape == (1, 4, S, S) and obs.dtype == torch.float32 and obs.is_cuda
+    assert len(env.meshes) == 3 and float(env.camera_position.abs().sum()) == 0.0
+    action = torch.nn.Parameter(torch.tensor([0.3, -1.0]))
+    obs, reward, finished, info = env.step(action)
+    assert obs.shape == (1, 4, S, S) and reward.dim() == 0 and finished.dtype == torch.bool and finished.dim() == 0
+    assert info["full_state"].shape == (1, S, S, 4) and info["position"].shape == (3,) and info["full_reward"].dim() == 0
+    reward.backward()
+    assert action.grad is not None and action.grad.shape == (2,) and torch.isfinite(action.grad).all()
+    assert float(action.grad.abs().sum()) > 0
+    # same numbers as the oracle env
+    sc = default_scene("teapot")
+    ref = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S)
+    ref.reset(azimuth=1.5)
+    _, r, d, _ = ref.step(np.array([0.3, -1.0], np.float32))
+    np.testing.assert_allclose(float(reward), float(r), rtol=RTOL, atol=2e-6)
+    assert bool(finished) == bool(d)
+    rgba, depth = env.render()
+    assert rgba.shape == (1, S, S, 4) and depth.shape == (1, S, S, 1)
+    np.testing.assert_allclose(rgba[0, ..., 0].cpu().numpy(), obs[0, 0].detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # numpy actions and no-grad path
+    o2, r2, f2, _ = env.step(np.array([0.0, 0.0], np.float32))
+    assert abs(float(r2) + 0.2) < 1e-6 or bool(f2)
+    env.close()
+
+
+def test_batched_vecenv_matches_sequential_reference_loop(oracle, cuda_lib):
+    """BatchedOcclusionVecEnv == the reference's SimpleVecEnv loop (SubProcVecEnv.py:203-220) incl. auto-reset."""
+    from occlusionenv_b200.SubProcVecEnv import BatchedOcclusionVecEnv
+    sc = default_scene("teapot")
+    S, n = 32, 5
+    venv = BatchedOcclusionVecEnv(n, data=None, img_size=S, keep_terminal_obs=True)
+    az0 = np.array([1.5, 0.0, 1.3, 1.8, 0.05], np.float32)  # envs 1 and 4 start (almost) unoccluded
+    obs = venv.reset(azimuth=torch.tensor(az0))
+    assert obs.shape == (n, 4, S, S)
+    refs = [oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S) for _ in range(n)]
+    ovec = oracle.OracleSimpleVecEnv(refs)
+    ovec.reset(azimuths=az0)
+    rng = np.random.default_rng(5)
+    for t in range(3):
+        a = rng.normal(size=(n, 2)).astype(np.float32)
+        obs, rews, dones, infos = venv.step(torch.tensor(a))
+        o_obs, o_rews, o_dones, o_infos = ovec.step(a)
+        assert obs.shape == (n, 4, S, S) and rews.shape == (n,) and dones.shape == (n,) and dones.dtype == torch.bool
+        assert len(infos) == n
+        assert np.array_equal(dones.cpu().numpy(), o_dones)
+        np.testing.assert_allclose(rews.cpu().numpy(), o_rews, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(obs.cpu().numpy(), o_obs, rtol=RTOL, atol=1e-6)
+        for e in range(n):
+            if o_dones[e]:
+                np.testing.assert_allclose(infos[e]["terminal_observation"][0].cpu().numpy(),
+                                           o_infos[e]["terminal_observation"][0], rtol=RTOL, atol=1e-6)
+                np.testing.assert_allclose(float(venv.engine.full_reward[e]), float(refs[e].fullReward), rtol=RTOL, atol=1e-6)
+        assert o_dones.any() or t > 0
+    # differentiable batched step (train_predict.py:48-52)
+    step = torch.nn.Parameter(torch.randn(n, 2, device="cuda"))
+    obs, rews, dones, infos = venv.step(step)
+    rews.sum().backward()
+    assert step.grad.shape == (n, 2) and torch.isfinite(step.grad).all()
+
+
+def test_simple_vecenv_reference_shapes(cuda_lib):
+    from occlusionenv_b200.SubProcVecEnv import SimpleVecEnv
+    from occlusionenv_b200.environment import OcclusionEnv
+    venv = SimpleVecEnv([lambda: OcclusionEnv(img_size=32) for _ in range(2)])
+    obs = venv.reset()
+    assert obs.shape == (2, 1, 4, 32, 32)  # reference quirk B-8
+    obs, rews, dones, infos = venv.step(torch.randn(2, 2))
+    assert obs.shape == (2, 4, 32, 32) and rews.shape == (2,) and dones.shape == (2,) and len(infos) == 2
+    assert venv.get_attr("step_size") == [0.05, 0.05]
+    venv.set_attr("step_size", 0.1, indices=0)
+    assert venv.get_attr("step_size") == [0.1, 0.05]
+    assert len(venv.get_images()) == 2
+    venv.close()
+
+
+def test_three_object_per_env_meshes(oracle, cuda_lib):
+    """Config-3 shape at test size: per-env procedural meshes, 3 objects in the ShapeNet layout; K=100 cut
+    is the common case here."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    S, n = 64, 2
+    scenes = [procedural_scene(s, n_obj=3, subdiv=3) for s in (11, 12)]
+    eng = OcclusionEngine(None, n, RasterConfig(image_size=S), debug_outputs=True, per_env_scenes=scenes)
+    az0 = np.array([0.4, -0.3], np.float32)
+    eng.reset(radius=4.0, azimuth=torch.tensor(az0), elevation=0.1)
+    act = np.array([[1.0, 0.5], [-0.3, 0.9]], np.float32)
+    eng.step(torch.tensor(act, device="cuda"))
+    st = eng.status.cpu().numpy()
+    assert not (st & (4 | 8)).any(), st
+    for e, sc in enumerate(scenes):
+        ref = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S)
+        ref.reset(radius=4.0, azimuth=az0[e], elevation=0.1)
+        _, rew, done, _ = ref.step(act[e])
+        if st[e] & 1:
+            continue  # z-clip flagged: triangle clipping not implemented, results not comparable
+        assert np.array_equal(eng.pix_to_face[e].cpu().numpy(), ref.last.pix_to_face)
+        assert np.array_equal(eng.nhits[e].cpu().numpy(), ref.last.nhits)
+        np.testing.assert_allclose(eng.alphas[e].cpu().numpy(), ref.last.alphas, rtol=RTOL, atol=ATOL_A)
+        np.testing.assert_allclose(float(eng.reward[e]), float(rew), rtol=RTOL, atol=2e-6)
+
+
+def test_tile_shapes_and_odd_image_size(oracle, cuda_lib):
+    """Ragged case: image size not a multiple of the tile; several tile shapes give identical results."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    sc = default_scene("box")
+    S = 50
+    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.1, 1.4, 4.0)
+    ref = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
+    Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
+    for tw, th in [(0, 0), (16, 16), (50, 8), (64, 32)]:
+        eng = OcclusionEngine(sc, 1, RasterConfig(image_size=S, tile_w=tw, tile_h=th), debug_outputs=True)
+        eng.render(Rt, Tt, Ct)
+        eng.check_status()
+        assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), ref.pix_to_face), (tw, th)
+        assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits)
+        np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
+        np.testing.assert_allclose(eng.obs[0].cpu().numpy(), ref.obs, rtol=RTOL, atol=1e-6)

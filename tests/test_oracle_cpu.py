@@ -1,0 +1,158 @@
+"""CPU suite: the oracle against its golden vectors, its independent dense restatement and the survey's
+float64 probe values.  (The reference has no tests or fixtures of its own: parity unpinned.)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from occlusionenv_b200.config import RasterConfig
+from occlusionenv_b200.meshes import default_scene, make_box
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_constants_match_product_config(oracle):
+    cfg = RasterConfig(image_size=128)
+    assert np.float32(cfg.blur_radius) == oracle.BLUR_RADIUS
+    assert np.float32(cfg.proj_scale) == oracle.PROJ_SCALE
+    assert np.float32(cfg.sigma) == oracle.SIGMA
+    assert abs(float(oracle.PROJ_SCALE) - 1.0 / np.tan(np.pi / 6)) < 1e-6
+    assert abs(float(oracle.BLUR_RADIUS) - np.log(9999.0) * 1e-4) < 1e-9
+
+
+def test_survey_probe_values(oracle):
+    """two-teapot scene at 128^2: loss 0.0000 at az=0 and ~621.5 at az=1.5."""
+    g = np.load(os.path.join(GOLD, "scene_teapot_128.npz"))
+    assert float(g["loss0"]) < 1e-4
+    assert abs(float(g["loss2"]) - 621.5) < 0.1
+
+
+@pytest.mark.parametrize("occ", ["teapot", "box"])
+def test_oracle_reproduces_golden(oracle, occ):
+    g = np.load(os.path.join(GOLD, f"scene_{occ}_128.npz"))
+    sc = default_scene(occ)
+    for k in (1, 2):
+        r = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 128, g[f"C{k}"], g[f"R{k}"], g[f"T{k}"])
+        assert np.array_equal(r.pix_to_face.astype(np.int16), g[f"pix_to_face{k}"])
+        assert np.array_equal(r.zbuf, g[f"zbuf{k}"])
+        assert np.array_equal(r.alphas, g[f"alphas{k}"])
+        assert np.array_equal(r.obs[0], g[f"rgb{k}"])
+        assert np.array_equal(r.n_covered, g[f"n_covered{k}"])
+        assert np.array_equal(r.n_visible, g[f"n_visible{k}"])
+        assert np.float32(r.loss) == g[f"loss{k}"]
+
+
+def test_pose_matches_dense(oracle):
+    from oracle import dense_torch as D
+    for az, el, act in [(1.5, 0.0, (0.3, -1.0)), (0.7, 0.3, (0.0, 0.0)), (2.0, -0.4, (1.0, 0.1))]:
+        e, a, C, R, T = oracle.pose_step(np.asarray(act, np.float32), el, az, 4.0)
+        e2, a2, C2, R2, T2 = D.pose_step(torch.tensor(act, dtype=torch.float64), torch.tensor(el, dtype=torch.float64),
+                                         torch.tensor(az, dtype=torch.float64), torch.tensor(4.0, dtype=torch.float64))
+        np.testing.assert_allclose(R, R2.numpy(), atol=1e-6)
+        np.testing.assert_allclose(T, T2.numpy(), atol=2e-6)
+        np.testing.assert_allclose(C, C2.numpy(), atol=2e-6)
+        assert abs(float(e) - float(e2)) < 1e-6 and abs(float(a) - float(a2)) < 1e-6
+        # R orthonormal, T = -R^T C
+        np.testing.assert_allclose(R.T @ R, np.eye(3), atol=1e-6)
+        np.testing.assert_allclose(T, -(R.T @ C), atol=1e-6)
+    C, R, T = oracle.pose_lookat(4.0, 0.4, 1.0)
+    C2, R2, T2 = D.pose_lookat(torch.tensor(4.0, dtype=torch.float64), torch.tensor(0.4, dtype=torch.float64),
+                               torch.tensor(1.0, dtype=torch.float64))
+    np.testing.assert_allclose(R, R2.numpy(), atol=1e-6)
+    np.testing.assert_allclose(C, C2.numpy(), atol=2e-6)
+
+
+def test_oracle_matches_dense_forward_and_fd_gradient(oracle):
+    """Oracle (a) vs oracle (b) at 32^2, and the autograd gradient of (b) vs central differences."""
+    from oracle import dense_torch as D
+    sc = default_scene("teapot")
+    S = 32
+    env = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S)
+    env.reset(azimuth=1.45, elevation=0.1)
+    prev, mass = float(env.fullReward), float(env.objectMass)
+    act = np.array([0.3, -1.0])
+    args = (0.1, 1.45, 4.0, prev, mass, float(oracle.PROJ_SCALE), float(oracle.BLUR_RADIUS), float(oracle.SIGMA))
+    r, loss, g, alphas = D.reward_and_grad(sc, S, act, *args)
+    _, rew, _, _ = env.step(act.astype(np.float32))
+    assert abs(loss - float(env.last.loss)) <= 1e-5 * max(1.0, loss)
+    assert abs((r - 0.2) - float(rew)) <= 1e-5
+    assert (np.abs(alphas - env.last.alphas) > 1e-4).sum() <= 2
+    h = 1e-4
+    fd = []
+    for i in range(2):
+        d = np.zeros(2)
+        d[i] = h
+        fd.append((D.reward_and_grad(sc, S, act + d, *args)[0] - D.reward_and_grad(sc, S, act - d, *args)[0]) / (2 * h))
+    np.testing.assert_allclose(g, fd, rtol=5e-3, atol=1e-5)
+    assert abs(np.dot(g, act)) < 1e-6 * np.linalg.norm(g) * np.linalg.norm(act) + 1e-9  # scale invariance
+
+
+def test_topk_rule_is_live_and_sorted(oracle):
+    """faces_per_pixel=100 overflows on the teapot (SURVEY headline 6); kept hits are the nearest by (z, idx)."""
+    sc = default_scene("teapot")
+    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.0, 1.5, 4.0)
+    v, f = sc.object(0)
+    vp = oracle.project(v, R, T)
+    fr = oracle.rasterize(vp, f, 128, oracle.BLUR_RADIUS, 100)
+    assert (fr.nhits > 100).sum() > 0
+    full = oracle.rasterize(vp, f, 128, oracle.BLUR_RADIUS, 160)
+    ys, xs = np.nonzero(fr.nhits > 100)
+    for y, x in zip(ys, xs):
+        z = fr.zbuf[y, x]
+        assert (z >= 0).all() and (np.diff(z) >= 0).all()
+        assert np.array_equal(fr.pix_to_face[y, x], full.pix_to_face[y, x, :100])
+    # empty pixels are -1 filled
+    y, x = np.argwhere(fr.nhits == 0)[0]
+    assert (fr.pix_to_face[y, x] == -1).all() and (fr.zbuf[y, x] == -1).all() and (fr.dists[y, x] == -1).all()
+
+
+def test_rasterize_backward_matches_dense_autograd(oracle):
+    """A.7 restated in C (reverse mode, per-face-vertex gradients) vs autograd of the dense formulation."""
+    from oracle import dense_torch as D
+    sc = default_scene("teapot")
+    v, f = sc.object(0)
+    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.1, 1.2, 4.0)
+    S, K = 32, 100
+    vp = oracle.project(v, R, T)
+    fr = oracle.rasterize(vp, f, S, oracle.BLUR_RADIUS, K)
+    rng = np.random.default_rng(0)
+    w = rng.uniform(0.5, 1.5, size=(S, S))
+    # L = sum_px w * alpha ;  dL/ddist_k = w * (1-alpha)/(1-p_k) * p_k (1-p_k) / sigma * (+1) ... via chain rule
+    sig = float(oracle.SIGMA)
+    prob = np.where(fr.pix_to_face >= 0, 1.0 / (1.0 + np.exp(fr.dists.astype(np.float64) / sig)), 0.0)
+    one_minus = 1.0 - prob
+    prod = one_minus.prod(axis=-1, keepdims=True)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        others = np.where(one_minus > 0, prod / one_minus, 0.0)
+    gd = w[..., None] * others * (-(prob * one_minus) / sig)
+    gv = oracle.rasterize_backward(vp, f, fr, gd.astype(np.float32))
+    vt = torch.tensor(vp, dtype=torch.float64, requires_grad=True)
+    alpha = D.soft_alpha_rows(vt, torch.tensor(f, dtype=torch.long), S, torch.arange(S), float(oracle.BLUR_RADIUS), sig, K)
+    (alpha * torch.tensor(w)).sum().backward()
+    ref = vt.grad.numpy()
+    scale = np.abs(ref[:, :2]).max()
+    assert np.abs(gv[:, :2] - ref[:, :2]).max() <= 2e-3 * scale
+
+
+def test_box_is_outward_wound():
+    v, f = make_box()
+    ctr = v.mean(0)
+    for a, b, c in f:
+        n = np.cross(v[b] - v[a], v[c] - v[a])
+        assert np.dot(n, (v[a] + v[b] + v[c]) / 3 - ctr) > 0
+    assert v.shape == (8, 3) and f.shape == (12, 3)
+
+
+def test_state_machine_golden_trajectory(oracle):
+    g = np.load(os.path.join(GOLD, "trajectory_teapot_64.npz"))
+    sc = default_scene("teapot")
+    env = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=64)
+    env.reset(radius=4.0, azimuth=1.45, elevation=0.1)
+    assert np.float32(env.fullReward) == g["loss0"] and np.float32(env.objectMass) == g["mass"]
+    for i, a in enumerate(g["actions"][:2]):
+        _, r, d, info = env.step(a)
+        assert np.float32(r) == g["rewards"][i] and bool(d) == bool(g["dones"][i])
+        assert np.float32(env.elevation) == g["elevations"][i] and np.float32(env.azimuth) == g["azimuths"][i]
+    # zero action: no move (environment.py:358), reward = -0.2 exactly
+    assert g["rewards"][2] == np.float32(-0.2)
