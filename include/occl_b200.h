@@ -64,6 +64,8 @@ typedef struct OcclConfig {
   float done_threshold;                     /* 0.1; environment.py:386 */
   float reward_done;                        /* +5;  environment.py:390 */
   float reward_step;                        /* -0.2; environment.py:392 (stored as +0.2, subtracted) */
+  int32_t debug_exact;                      /* 1: evaluate every (pixel, face) pair with the reference's exact
+                                               operation sequence (no guarded fast path); for parity tests */
 } OcclConfig;
 
 /* Scene mesh in HBM. verts: (V,3) f32 world coordinates, faces: (F,3) i32 into verts.

@@ -29,6 +29,7 @@ class OcclConfig(Structure):
         ("blur_radius", c_float), ("sigma", c_float), ("proj_scale", c_float), ("z_clip", c_float),
         ("step_size", c_float), ("light", c_float * 3),
         ("done_threshold", c_float), ("reward_done", c_float), ("reward_step", c_float),
+        ("debug_exact", c_int32),
     ]
 
 

@@ -33,6 +33,7 @@ class RasterConfig:
     norm_with_object_size: bool = False          # :208
     tile_w: int = 0                              # CTA tile (0 = automatic)
     tile_h: int = 0
+    debug_exact: bool = False                    # every pair through the reference-order arithmetic (tests)
 
     @property
     def blur_radius(self) -> float:

@@ -30,6 +30,7 @@
 #define SCAN_CHUNK OCCL_THREADS
 #define BIG_FACE_PX 192       // faces covering more tile pixels than this are rasterised by the whole CTA
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
+#define DEFER_CAP 2048        // queued inside hits (exact depth resolved in a dense pass)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
 #define REC_WORDS 16
 
@@ -229,13 +230,13 @@ __global__ void project_kernel(long long total, int V, const float* __restrict__
 }
 
 // ----------------------------------------------------------------------------------------------
-// kernel 2-5: tile rasteriser
+// kernels 2-5: face setup / binning and the tile rasteriser
 // ----------------------------------------------------------------------------------------------
 struct RasterParams {
-  int S, n_obj, V, F, K, cull;
+  int S, n_obj, V, F, K, cull, exact_only;
   int obj_face_start[OCCL_MAX_OBJ + 1];
   int tile_w, tile_h, tiles_x, tiles_y;
-  float blur, bbox_r, sigma;
+  float blur, bbox_r, sigma, neg_inv_sigma, inv_sigma, band;
   float light[3];
   const float4* vproj;
   const float4* vtan;
@@ -245,6 +246,10 @@ struct RasterParams {
   long long faces_stride;
   const float* cam;
   Partial* partials;
+  // per-env compacted live faces (written by face_setup_kernel)
+  uint4* geo;    // [N][F][4]  16 words per live face, see REC_* below
+  uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16)
+  int* n_live;   // [N]
   // outputs
   float* obs;
   float* occl;
@@ -255,6 +260,15 @@ struct RasterParams {
   uint32_t* status;
   const uint8_t* env_mask;
 };
+
+// Record of a live face (16 words). Words 0..9 and 12..14 are floats.
+//   0..8  x0 y0 z0 x1 y1 z1 x2 y2 z2     (x_ndc, y_ndc, z_view)
+//   9     area = (float)((double)EdgeFunction(v2,v0,v1) + kEpsilon)
+//   10    packed face index | FAST flag in bit 31
+//   11    (tile list only) hard pixel range, tile-local, 8 bits each: x0 x1 y0 y1
+//   12..14  1/l2 of the edges v0v1, v0v2, v1v2  (fast path only)
+//   15    (tile list only) soft pixel range, tile-local, 8 bits each
+#define REC_FAST 0x80000000u
 
 struct FaceGeo {
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
@@ -302,7 +316,8 @@ __device__ __forceinline__ void bary_persp(const FaceGeo& g, float px, float py,
   *b2 = t2 / den;
 }
 
-__device__ __forceinline__ PairResult eval_pair(const FaceGeo& g, float px, float py) {
+// The reference rule, operation for operation.
+__device__ __noinline__ PairResult eval_pair(const FaceGeo& g, float px, float py) {
   PairResult r;
   bary_persp(g, px, py, &r.b0, &r.b1, &r.b2);
   r.inside = r.b0 > 0.f && r.b1 > 0.f && r.b2 > 0.f;
@@ -341,8 +356,9 @@ __device__ __forceinline__ float soft_prob(float signed_dist, float sigma) {
 }
 
 // Exact pixel range of an NDC interval [lo, hi]: pixels whose centre c satisfies !(c>hi) && !(c<lo).
-// Pixel centres DEcrease with the index: c(i) = pix_to_ndc(S-1-i).
-__device__ __forceinline__ void ndc_range_to_pixels(float lo, float hi, int S, int* i0, int* i1) {
+// Pixel centres DEcrease with the index; tab[i] = pix_to_ndc(S-1-i, S) (exact reference values).
+__device__ __forceinline__ void ndc_range_to_pixels(const float* __restrict__ tab, float lo, float hi,
+                                                    int S, int* i0, int* i1) {
   const float fS = (float)S;
   float e0 = ceilf(((1.0f - hi) * fS - 1.0f) * 0.5f) - 1.0f;
   float e1 = floorf(((1.0f - lo) * fS - 1.0f) * 0.5f) + 1.0f;
@@ -351,27 +367,17 @@ __device__ __forceinline__ void ndc_range_to_pixels(float lo, float hi, int S, i
   int a = (int)e0, b = (int)e1;
   if (!(e0 == e0)) a = 0;
   if (!(e1 == e1)) b = S - 1;
-  while (a < S && pix_to_ndc(S - 1 - a, S) > hi) ++a;
-  while (a > 0 && !(pix_to_ndc(S - 1 - (a - 1), S) > hi)) --a;
-  while (b >= 0 && pix_to_ndc(S - 1 - b, S) < lo) --b;
-  while (b < S - 1 && !(pix_to_ndc(S - 1 - (b + 1), S) < lo)) ++b;
+  while (a < S && tab[a] > hi) ++a;
+  while (a > 0 && !(tab[a - 1] > hi)) --a;
+  while (b >= 0 && tab[b] < lo) --b;
+  while (b < S - 1 && !(tab[b + 1] < lo)) ++b;
   *i0 = a;
   *i1 = b;
 }
 
-struct FaceSetup {
-  FaceGeo g;
-  bool live;
-  int sx0, sx1, sy0, sy1;  // soft (blur-expanded) pixel range, image coordinates
-  int hx0, hx1, hy0, hy1;  // hard (blur = 0) pixel range
-  float xmin, xmax, ymin, ymax;  // blur-expanded NDC bounding box
-};
-
-// Pixel-independent part of CheckPixelInsideFace: culls + the two bounding boxes.
-template <bool RANGES>
-__device__ __forceinline__ void setup_face(const float4 a, const float4 b, const float4 c, int S,
-                                           float bbox_r, int cull, FaceSetup* fs) {
-  FaceGeo& g = fs->g;
+// Pixel-independent part of CheckPixelInsideFace: the culls and `area`.
+__device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const float4 c, int cull, FaceGeo* gp) {
+  FaceGeo& g = *gp;
   g.x0 = a.x; g.y0 = a.y; g.z0 = a.z;
   g.x1 = b.x; g.y1 = b.y; g.z1 = b.z;
   g.x2 = c.x; g.y2 = c.y; g.z2 = c.z;
@@ -383,22 +389,107 @@ __device__ __forceinline__ void setup_face(const float4 a, const float4 b, const
   skip |= (cull && face_area < 0.f);
   skip |= ((double)face_area <= 1e-8 && (double)face_area >= -1e-8);
   skip |= ((double)zmin < 1e-8);
-  fs->live = !skip;
-  if (skip) return;
+  if (skip) return false;
   // area = EdgeFunctionForward(v2, v0, v1) + kEpsilon   (kEpsilon is a double)
   const float e = (g.x2 - g.x0) * (g.y1 - g.y0) - (g.y2 - g.y0) * (g.x1 - g.x0);
   g.area = (float)((double)e + 1e-8);
-  const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
-  const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
-  fs->xmin = xlo - bbox_r; fs->xmax = xhi + bbox_r;
-  fs->ymin = ylo - bbox_r; fs->ymax = yhi + bbox_r;
-  if (!RANGES) return;
-  ndc_range_to_pixels(xlo - bbox_r, xhi + bbox_r, S, &fs->sx0, &fs->sx1);
-  ndc_range_to_pixels(ylo - bbox_r, yhi + bbox_r, S, &fs->sy0, &fs->sy1);
-  ndc_range_to_pixels(xlo - 0.0f, xhi + 0.0f, S, &fs->hx0, &fs->hx1);
-  ndc_range_to_pixels(ylo - 0.0f, yhi + 0.0f, S, &fs->hy0, &fs->hy1);
+  return true;
 }
 
+// ----------------------------------------------------------------------------------------------
+// kernel 2: per-env face setup + ordered compaction of the live faces
+// ----------------------------------------------------------------------------------------------
+struct SetupParams {
+  int S, V, F, cull;
+  float bbox_r;
+  const float4* vproj;
+  const int* faces;
+  long long faces_stride;
+  uint4* geo;
+  uint4* rng;
+  int* n_live;
+  const uint8_t* env_mask;
+};
+
+__global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* tab = (float*)smem_raw;  // [S] pixel-centre table
+  __shared__ int s_wcnt[OCCL_WARPS];
+  __shared__ int s_base;
+  const int env = blockIdx.x;
+  if (p.env_mask && !p.env_mask[env]) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = p.S;
+  for (int i = tid; i < S; i += OCCL_THREADS) tab[i] = pix_to_ndc(S - 1 - i, S);
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
+  const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
+  uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
+  uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
+  for (int base = 0; base < p.F; base += OCCL_THREADS) {
+    const int f = base + tid;
+    bool live = false;
+    FaceGeo g;
+    int sx0 = 0, sx1 = -1, sy0 = 0, sy1 = -1, hx0 = 0, hx1 = -1, hy0 = 0, hy1 = -1;
+    if (f < p.F) {
+      const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+      live = face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, &g);
+      if (live) {
+        const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
+        const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
+        ndc_range_to_pixels(tab, xlo - p.bbox_r, xhi + p.bbox_r, S, &sx0, &sx1);
+        ndc_range_to_pixels(tab, ylo - p.bbox_r, yhi + p.bbox_r, S, &sy0, &sy1);
+        live = sx0 <= sx1 && sy0 <= sy1;  // faces whose blur box misses every pixel centre
+        if (live) {
+          ndc_range_to_pixels(tab, xlo - 0.0f, xhi + 0.0f, S, &hx0, &hx1);
+          ndc_range_to_pixels(tab, ylo - 0.0f, yhi + 0.0f, S, &hy0, &hy1);
+          if (hx0 > hx1 || hy0 > hy1) { hx0 = 0xffff; hx1 = 0; hy0 = 0xffff; hy1 = 0; }
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base, total = 0;
+#pragma unroll
+    for (int w = 0; w < OCCL_WARPS; ++w) {
+      const int c = s_wcnt[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (live) {
+      const int slot = off + __popc(bal & ((1u << lane) - 1u));
+      // fast-path guards (see eval_fast): magnitudes for which sign(b_i) == sign(e_i) provably and the
+      // approximate edge distances stay inside the decision band
+      const float bx01 = g.x1 - g.x0, by01 = g.y1 - g.y0, bx02 = g.x2 - g.x0, by02 = g.y2 - g.y0;
+      const float bx12 = g.x2 - g.x1, by12 = g.y2 - g.y1;
+      const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
+      const float zmax = fmaxf(fmaxf(g.z0, g.z1), g.z2), zmin = fminf(fminf(g.z0, g.z1), g.z2);
+      const float cmax = fmaxf(fmaxf(fmaxf(fabsf(g.x0), fabsf(g.x1)), fabsf(g.x2)),
+                               fmaxf(fmaxf(fabsf(g.y0), fabsf(g.y1)), fabsf(g.y2)));
+      const bool fast = g.area >= 9.094947e-13f /*2^-40*/ && g.area <= 1024.f && zmin >= 9.765625e-4f && zmax <= 1024.f &&
+                        cmax <= 4.0f && l01 > 1e-8f && l02 > 1e-8f && l12 > 1e-8f;
+      uint4 q0, q1, q2, q3;
+      q0 = make_uint4(__float_as_uint(g.x0), __float_as_uint(g.y0), __float_as_uint(g.z0), __float_as_uint(g.x1));
+      q1 = make_uint4(__float_as_uint(g.y1), __float_as_uint(g.z1), __float_as_uint(g.x2), __float_as_uint(g.y2));
+      q2 = make_uint4(__float_as_uint(g.z2), __float_as_uint(g.area), (uint32_t)f | (fast ? REC_FAST : 0u), 0u);
+      q3 = make_uint4(__float_as_uint(1.0f / l01), __float_as_uint(1.0f / l02), __float_as_uint(1.0f / l12), 0u);
+      uint4* o = geo + (size_t)slot * 4;
+      o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
+      rng[slot] = make_uint4((uint32_t)sx0 | ((uint32_t)sx1 << 16), (uint32_t)sy0 | ((uint32_t)sy1 << 16),
+                             (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16));
+    }
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
+  }
+  if (tid == 0) p.n_live[env] = s_base;
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernels 3-5: tile rasteriser
+// ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
   int o = 0;
 #pragma unroll
@@ -428,66 +519,140 @@ struct TileSmem {
   float* ndc_x;              // [tile_w]
   float* ndc_y;              // [tile_h]
   uint32_t* list;            // [LIST_CAP][REC_WORDS]  (aliased by the top-K selection buffers)
+  uint32_t* defer;           // [DEFER_CAP] inside hits of small faces awaiting their exact depth
+  int* defer_n;
 };
 
-template <bool GRAD>
+__device__ __forceinline__ void load_geo(const uint32_t* __restrict__ rec, FaceGeo* g) {
+  g->x0 = __uint_as_float(rec[0]); g->y0 = __uint_as_float(rec[1]); g->z0 = __uint_as_float(rec[2]);
+  g->x1 = __uint_as_float(rec[3]); g->y1 = __uint_as_float(rec[4]); g->z1 = __uint_as_float(rec[5]);
+  g->x2 = __uint_as_float(rec[6]); g->y2 = __uint_as_float(rec[7]); g->z2 = __uint_as_float(rec[8]);
+  g->area = __uint_as_float(rec[9]);
+}
+
+// exact depth of an inside hit -> nearest-face key
+__device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g, int fidx, int pix, float px,
+                                            float py, float b0, float b1, float b2, bool have_bary) {
+  if (!have_bary) bary_persp(g, px, py, &b0, &b1, &b2);
+  const float pz = b0 * g.z0 + b1 * g.z1 + b2 * g.z2;
+  if (!(pz < 0.f)) {
+    const unsigned long long key =
+        ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)fidx;
+    atomicMin(sm.hard + pix, key);
+  }
+}
+
+// One face against the pixels of its (tile-clipped) blur box; `nlanes` threads stride over them.
+// DEFER: inside hits are queued for a dense exact-depth pass instead of being resolved in the
+// divergent loop.
+template <bool GRAD, bool DEFER>
 __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, int tpx,
-                                                   const uint32_t* __restrict__ rec, int env, int lane,
-                                                   int nlanes) {
+                                                   const uint32_t* __restrict__ rec, int slot_id, int env,
+                                                   int lane, int nlanes) {
   FaceGeo g;
-  g.x0 = __uint_as_float(rec[0]); g.y0 = __uint_as_float(rec[1]); g.z0 = __uint_as_float(rec[2]);
-  g.x1 = __uint_as_float(rec[3]); g.y1 = __uint_as_float(rec[4]); g.z1 = __uint_as_float(rec[5]);
-  g.x2 = __uint_as_float(rec[6]); g.y2 = __uint_as_float(rec[7]); g.z2 = __uint_as_float(rec[8]);
-  g.area = __uint_as_float(rec[9]);
-  const int fidx = (int)rec[10];
-  const uint32_t sb = rec[11], hb = rec[12];
+  load_geo(rec, &g);
+  const uint32_t w10 = rec[10];
+  const int fidx = (int)(w10 & 0x7fffffffu);
+  const bool fast_face = (w10 & REC_FAST) != 0u && !p.exact_only;
+  const uint32_t sb = rec[15], hb = rec[11];
   const int lx0 = sb & 0xff, lx1 = (sb >> 8) & 0xff, ly0 = (sb >> 16) & 0xff, ly1 = (sb >> 24) & 0xff;
   const int hx0 = hb & 0xff, hx1 = (hb >> 8) & 0xff, hy0 = (hb >> 16) & 0xff, hy1 = (hb >> 24) & 0xff;
   const int obj = obj_of_face(p, fidx);
   const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
   const int n = w * h;
+  const float inv_w = 1.0f / (float)w;
+  // per-face uniforms of the fast path
+  const float bx01 = g.x1 - g.x0, by01 = g.y1 - g.y0;
+  const float bx02 = g.x2 - g.x0, by02 = g.y2 - g.y0;
+  const float bx12 = g.x2 - g.x1, by12 = g.y2 - g.y1;
+  const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
   float4 ta, tb, tc;
   if (GRAD) {
     const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-    ta = __ldg(vt + rec[13]);
-    tb = __ldg(vt + rec[14]);
-    tc = __ldg(vt + rec[15]);
+    const int* __restrict__ fc = p.faces + (size_t)env * p.faces_stride + 3 * (size_t)fidx;
+    ta = __ldg(vt + __ldg(fc + 0));
+    tb = __ldg(vt + __ldg(fc + 1));
+    tc = __ldg(vt + __ldg(fc + 2));
   }
   unsigned long long* soft = sm.soft + (size_t)obj * tpx;
   for (int i = lane; i < n; i += nlanes) {
-    const int ry = i / w;
+    const int ry = (int)(((float)i + 0.5f) * inv_w);
     const int rx = i - ry * w;
     const int lx = lx0 + rx, ly = ly0 + ry;
     const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
-    const PairResult r = eval_pair(g, px, py);
-    if (!r.inside && r.dist >= p.blur) continue;
+    bool inside, have_bary = false;
+    float dist, tt, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    int edge;
+    bool need_exact = !fast_face;
+    if (fast_face) {
+      const float dx0 = px - g.x0, dy0 = py - g.y0, dx1 = px - g.x1, dy1 = py - g.y1, dx2 = px - g.x2, dy2 = py - g.y2;
+      // edge functions in the reference's rounding (separate multiply / subtract: this TU has -fmad=false)
+      const float e0 = dx1 * by12 - dy1 * bx12;
+      const float e1 = dy2 * bx02 - dx2 * by02;
+      const float e2 = dx0 * by01 - dy0 * bx01;
+      const float a0 = fabsf(e0), a1 = fabsf(e1), a2 = fabsf(e2);
+      const float emax = fmaxf(fmaxf(a0, a1), a2), emin = fminf(fminf(a0, a1), a2);
+      // sign(b_i) == sign(e_i) when no quotient can underflow (face guards + this spread guard)
+      const bool sign_ok = emax >= 9.313226e-10f /*2^-30*/ && emin >= 9.313226e-10f * emax;
+      inside = e0 > 0.f && e1 > 0.f && e2 > 0.f;
+      // squared distances to the three edges in the reference's operation order (bit-identical to
+      // seg_dist for non-degenerate edges, which the FAST flag guarantees): sigmoid(-d/sigma) has slope
+      // 1/sigma = 1e4, so even a 1-ulp change of a projected point would move alpha by > 1e-5 relative
+      const float t01 = fminf(fmaxf((bx01 * dx0 + by01 * dy0) / l01, 0.0f), 1.0f);
+      const float t02 = fminf(fmaxf((bx02 * dx0 + by02 * dy0) / l02, 0.0f), 1.0f);
+      const float t12 = fminf(fmaxf((bx12 * dx1 + by12 * dy1) / l12, 0.0f), 1.0f);
+      const float ux01 = px - (g.x0 + t01 * bx01), uy01 = py - (g.y0 + t01 * by01);
+      const float ux02 = px - (g.x0 + t02 * bx02), uy02 = py - (g.y0 + t02 * by02);
+      const float ux12 = px - (g.x1 + t12 * bx12), uy12 = py - (g.y1 + t12 * by12);
+      const float d01 = ux01 * ux01 + uy01 * uy01;
+      const float d02 = ux02 * ux02 + uy02 * uy02;
+      const float d12 = ux12 * ux12 + uy12 * uy12;
+      dist = fminf(fminf(d01, d02), d12);
+      if (d01 <= d02 && d01 <= d12) { edge = 0; tt = t01; }
+      else if (d02 <= d12) { edge = 1; tt = t02; }
+      else { edge = 2; tt = t12; }
+      // only the inside test is shortcut (signs of the edge functions instead of six divisions)
+      need_exact = !sign_ok;
+    }
+    if (need_exact) {
+      const PairResult r = eval_pair(g, px, py);
+      inside = r.inside; dist = r.dist; tt = r.t; edge = r.edge;
+      b0 = r.b0; b1 = r.b1; b2 = r.b2;
+      have_bary = true;
+    }
+    if (!inside && dist >= p.blur) continue;
     const int pix = ly * p.tile_w + lx;
-    const float sd = r.inside ? -r.dist : r.dist;
-    const float prob = soft_prob(sd, p.sigma);
-    const bool hard_ok = r.inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
+    const float sd = inside ? -dist : dist;
+    float prob;
+    if (need_exact) prob = soft_prob(sd, p.sigma);
+    else prob = __frcp_rn(1.0f + __expf(sd * p.inv_sigma));  // sigmoid(-sd/sigma)
+    const bool hard_ok = inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
     soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
     if (hard_ok) {
-      const float pz = r.b0 * g.z0 + r.b1 * g.z1 + r.b2 * g.z2;
-      if (!(pz < 0.f)) {
-        const unsigned long long key =
-            ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)fidx;
-        atomicMin(sm.hard + pix, key);
+      bool queued = false;
+      if (DEFER && !have_bary) {
+        const int d = atomicAdd(sm.defer_n, 1);
+        if (d < DEFER_CAP) {
+          sm.defer[d] = (uint32_t)pix | ((uint32_t)slot_id << 16);
+          queued = true;
+        }
       }
+      if (!queued) hard_update(sm, g, fidx, pix, px, py, b0, b1, b2, have_bary);
     }
     if (GRAD) {
       // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
       float ax, ay, bx, by;
       float4 da, db;
-      if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
-      else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+      if (edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+      else if (edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
       else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
-      const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
-      const float sgn = r.inside ? -1.f : 1.f;
+      const float qx = ax + tt * (bx - ax), qy = ay + tt * (by - ay);
+      const float sgn = inside ? -1.f : 1.f;
       const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
-      const float wa = 1.f - r.t, wb = r.t;
+      const float wa = 1.f - tt, wb = tt;
       const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
       const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
-      const float k = prob / p.sigma;
+      const float k = prob * p.inv_sigma;
       float* ga = sm.gacc + (size_t)obj * 2 * tpx;
       atomicAdd(ga + pix, k * dsd_el);
       atomicAdd(ga + tpx + pix, k * dsd_az);
@@ -507,7 +672,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(OCCL_THREADS)
+__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 2 : 3)
 raster_kernel(const RasterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -520,21 +685,24 @@ raster_kernel(const RasterParams p) {
   const int tpx = p.tile_w * p.tile_h;
   const int S = p.S;
 
+  __shared__ int s_list_n, s_next, s_big_n, s_ovf_n, s_hit_n, s_defer_n;
+  __shared__ int s_big[LIST_CAP];
+  __shared__ int s_ovf[OVF_CAP];
+  __shared__ double s_red[OCCL_WARPS][4];
+  __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
+
   TileSmem sm;
   {
     unsigned char* q = smem_raw;
     sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
     sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
     sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * LIST_CAP * REC_WORDS;
+    sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * DEFER_CAP;
     sm.gacc = (float*)q;               if (GRAD) q += sizeof(float) * 2 * tpx * p.n_obj;
     sm.ndc_x = (float*)q;              q += sizeof(float) * p.tile_w;
     sm.ndc_y = (float*)q;
+    sm.defer_n = &s_defer_n;
   }
-  __shared__ int s_list_n, s_next, s_big_n, s_ovf_n, s_hit_n;
-  __shared__ int s_big[LIST_CAP];
-  __shared__ int s_ovf[OVF_CAP];
-  __shared__ double s_red[OCCL_WARPS][4];
-  __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
 
   // ---- init accumulators -------------------------------------------------------------------
   for (int i = tid; i < tpx; i += OCCL_THREADS) sm.hard[i] = ~0ull;
@@ -543,29 +711,27 @@ raster_kernel(const RasterParams p) {
     for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
   for (int i = tid; i < p.tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < p.tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_ovf_n = 0; s_hit_n = 0; }
+  if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_ovf_n = 0; s_hit_n = 0; s_defer_n = 0; }
   __syncthreads();
 
   const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
+  const uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
+  const uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
+  const int n_live = p.n_live[env];
+  const int tx1 = tx0 + p.tile_w - 1, ty1 = ty0 + p.tile_h - 1;
 
-  // ---- face scan -> compacted list -> scatter ------------------------------------------------
-  for (int base = 0; base < p.F; base += SCAN_CHUNK) {
-    const int f = base + tid;
+  // ---- scan the env's live faces -> tile list in shared memory (warp-ballot compaction) -> scatter ----
+  for (int base = 0; base < n_live; base += SCAN_CHUNK) {
+    const int k = base + tid;
     bool keep = false;
-    FaceSetup fs;
-    int i0 = 0, i1 = 0, i2 = 0;
     int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
-    if (f < p.F) {
-      i0 = __ldg(faces + 3 * f + 0);
-      i1 = __ldg(faces + 3 * f + 1);
-      i2 = __ldg(faces + 3 * f + 2);
-      setup_face<true>(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), S, p.bbox_r, p.cull, &fs);
-      if (fs.live) {
-        cx0 = max(fs.sx0, tx0);  cx1 = min(fs.sx1, tx0 + p.tile_w - 1);
-        cy0 = max(fs.sy0, ty0);  cy1 = min(fs.sy1, ty0 + p.tile_h - 1);
-        keep = cx0 <= cx1 && cy0 <= cy1;
-      }
+    uint4 rg = make_uint4(0, 0, 0, 0);
+    if (k < n_live) {
+      rg = __ldg(rng + k);
+      cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
+      cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
+      keep = cx0 <= cx1 && cy0 <= cy1;
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     int slot0 = 0;
@@ -573,24 +739,20 @@ raster_kernel(const RasterParams p) {
     slot0 = __shfl_sync(0xffffffffu, slot0, 0);
     if (keep) {
       const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-      uint32_t* rec = sm.list + slot * REC_WORDS;
-      rec[0] = __float_as_uint(fs.g.x0); rec[1] = __float_as_uint(fs.g.y0); rec[2] = __float_as_uint(fs.g.z0);
-      rec[3] = __float_as_uint(fs.g.x1); rec[4] = __float_as_uint(fs.g.y1); rec[5] = __float_as_uint(fs.g.z1);
-      rec[6] = __float_as_uint(fs.g.x2); rec[7] = __float_as_uint(fs.g.y2); rec[8] = __float_as_uint(fs.g.z2);
-      rec[9] = __float_as_uint(fs.g.area);
-      rec[10] = (uint32_t)f;
-      rec[11] = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
-                ((uint32_t)(cy1 - ty0) << 24);
-      // hard range clipped to the tile; empty -> x0 = 255, x1 = 0
-      int hx0 = max(fs.hx0, tx0) - tx0, hx1 = min(fs.hx1, tx0 + p.tile_w - 1) - tx0;
-      int hy0 = max(fs.hy0, ty0) - ty0, hy1 = min(fs.hy1, ty0 + p.tile_h - 1) - ty0;
+      const uint4* __restrict__ src = geo + (size_t)k * 4;
+      uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+      int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)(rg.z >> 16), tx1) - tx0;
+      int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)(rg.w >> 16), ty1) - ty0;
       if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
-      rec[12] = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
-      rec[13] = (uint32_t)i0; rec[14] = (uint32_t)i1; rec[15] = (uint32_t)i2;
+      q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
+      q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
+             ((uint32_t)(cy1 - ty0) << 24);
+      uint4* dst = (uint4*)(sm.list + slot * REC_WORDS);
+      dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
       if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > BIG_FACE_PX) s_big[atomicAdd(&s_big_n, 1)] = slot;
     }
     __syncthreads();
-    const bool last = base + SCAN_CHUNK >= p.F;
+    const bool last = base + SCAN_CHUNK >= n_live;
     const int n = s_list_n;
     __syncthreads();  // everyone has read the count before the next round may append
     if (n > LIST_CAP - SCAN_CHUNK || last) {
@@ -601,17 +763,29 @@ raster_kernel(const RasterParams p) {
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i >= n) break;
         const uint32_t* rec = sm.list + i * REC_WORDS;
-        const uint32_t sb = rec[11];
+        const uint32_t sb = rec[15];
         const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
         if (npx > BIG_FACE_PX) continue;
-        raster_face_pixels<GRAD>(p, sm, tpx, rec, env, lane, 32);
+        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, i, env, lane, 32);
       }
       __syncthreads();
+      // dense exact-depth pass over the queued inside hits
+      const int nd = min(s_defer_n, DEFER_CAP);
+      for (int j = tid; j < nd; j += OCCL_THREADS) {
+        const uint32_t d = sm.defer[j];
+        const int pix = (int)(d & 0xffffu);
+        const uint32_t* rec = sm.list + (d >> 16) * REC_WORDS;
+        FaceGeo g;
+        load_geo(rec, &g);
+        const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
+        hard_update(sm, g, (int)(rec[10] & 0x7fffffffu), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
+      }
       // big faces: the whole CTA on one face at a time
       const int nb = s_big_n;
-      for (int b = 0; b < nb; ++b) raster_face_pixels<GRAD>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, env, tid, OCCL_THREADS);
+      for (int b = 0; b < nb; ++b)
+        raster_face_pixels<GRAD, false>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, s_big[b], env, tid, OCCL_THREADS);
       __syncthreads();
-      if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; }
+      if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_defer_n = 0; }
       __syncthreads();
     }
   }
@@ -633,7 +807,7 @@ raster_kernel(const RasterParams p) {
     unsigned long long* hkey = (unsigned long long*)sm.list;            // [HIT_CAP]
     float* hq = (float*)(hkey + HIT_CAP);                               // [HIT_CAP]
     float* hg = hq + HIT_CAP;                                           // [2][HIT_CAP] (GRAD)
-    // deterministic order of the overflow list (atomicAdd order is not): sort small list by value
+    // deterministic order of the overflow list (atomicAdd order is not): sort the small list
     if (tid == 0) {
       for (int a = 1; a < n_ovf; ++a) {
         const int v = s_ovf[a];
@@ -652,14 +826,22 @@ raster_kernel(const RasterParams p) {
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
       if (tid == 0) s_hit_n = 0;
       __syncthreads();
-      for (int f = p.obj_face_start[obj] + tid; f < p.obj_face_start[obj + 1]; f += OCCL_THREADS) {
-        const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
-        FaceSetup fs;
-        setup_face<false>(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), S, p.bbox_r, p.cull, &fs);
-        if (!fs.live || px > fs.xmax || px < fs.xmin || py > fs.ymax || py < fs.ymin) continue;
-        const PairResult r = eval_pair(fs.g, px, py);
+      // candidates: live faces of this object whose blur box holds the pixel (exact integer ranges)
+      for (int k = tid; k < n_live; k += OCCL_THREADS) {
+        const uint4 rg = __ldg(rng + k);
+        if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
+        const uint4* __restrict__ src = geo + (size_t)k * 4;
+        const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+        const int f = (int)(q2.z & 0x7fffffffu);
+        if (f < p.obj_face_start[obj] || f >= p.obj_face_start[obj + 1]) continue;
+        FaceGeo g;
+        g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+        g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+        g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+        g.area = __uint_as_float(q2.y);
+        const PairResult r = eval_pair(g, px, py);
         if (!r.inside && r.dist >= p.blur) continue;
-        const float pz = pz_clipped(fs.g, r.b0, r.b1, r.b2);
+        const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
         const float sd = r.inside ? -r.dist : r.dist;
         const float prob = soft_prob(sd, p.sigma);
         const int h = atomicAdd(&s_hit_n, 1);
@@ -668,10 +850,10 @@ raster_kernel(const RasterParams p) {
           hq[h] = 1.0f - prob;
           if (GRAD) {
             const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-            const float4 ta = __ldg(vt + i0), tb = __ldg(vt + i1), tc = __ldg(vt + i2);
+            const float4 ta = __ldg(vt + __ldg(faces + 3 * f + 0)), tb = __ldg(vt + __ldg(faces + 3 * f + 1)),
+                         tc = __ldg(vt + __ldg(faces + 3 * f + 2));
             float ax, ay, bx, by;
             float4 da, db;
-            const FaceGeo& g = fs.g;
             if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
             else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
             else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
@@ -679,9 +861,9 @@ raster_kernel(const RasterParams p) {
             const float sgn = r.inside ? -1.f : 1.f;
             const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
             const float wa = 1.f - r.t, wb = r.t;
-            const float k = prob / p.sigma;
-            hg[h] = k * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
-            hg[HIT_CAP + h] = k * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+            const float kk = prob / p.sigma;
+            hg[h] = kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+            hg[HIT_CAP + h] = kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
           }
         }
       }
@@ -948,13 +1130,13 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, total;
   int n_tiles;
 };
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
-  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * LIST_CAP * REC_WORDS;
+  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * LIST_CAP * REC_WORDS + 4 * DEFER_CAP;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
   b += 4 * (size_t)(c->tile_w + c->tile_h);
   return b;
@@ -994,6 +1176,9 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->vproj = off;    off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
   L->vtan = off;     if (with_grad) off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
   L->partials = off; off = align_up(off + sizeof(Partial) * (size_t)n * L->n_tiles, 256);
+  L->geo = off;      off = align_up(off + sizeof(uint4) * 4 * (size_t)n * c->n_faces, 256);
+  L->rng = off;      off = align_up(off + sizeof(uint4) * (size_t)n * c->n_faces, 256);
+  L->n_live = off;   off = align_up(off + sizeof(int) * (size_t)n, 256);
   L->total = off;
   return 0;
 }
@@ -1091,6 +1276,11 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.tiles_x = (c.image_size + c.tile_w - 1) / c.tile_w;
   p.tiles_y = (c.image_size + c.tile_h - 1) / c.tile_h;
   p.blur = c.blur_radius; p.bbox_r = sqrtf(c.blur_radius); p.sigma = c.sigma;
+  p.inv_sigma = 1.0f / c.sigma; p.neg_inv_sigma = -p.inv_sigma;
+  // decision band of the fast path: |dist_fast - dist_reference| < ~2e-8 for |coords| <= 4
+  p.band = 4e-5f * p.bbox_r;
+  p.exact_only = c.debug_exact;
+  p.geo = (uint4*)(base + L.geo); p.rng = (uint4*)(base + L.rng); p.n_live = (int*)(base + L.n_live);
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
   p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
@@ -1103,6 +1293,14 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   const size_t smem = tile_smem_bytes(&c, grad);
   const long long blocks = (long long)n * L.n_tiles;
   if (blocks > 0x7fffffffLL) return OCCL_E_INVALID;
+  {
+    SetupParams sp;
+    sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
+    sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
+    sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
+    face_setup_kernel<<<n, OCCL_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    CK(cudaGetLastError(), "face_setup_kernel");
+  }
   if (grad) {
     CK(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
     raster_kernel<true><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);

@@ -71,6 +71,7 @@ class OcclusionEngine:
         c.done_threshold = cfg.done_threshold
         c.reward_done = cfg.reward_done
         c.reward_step = cfg.reward_step
+        c.debug_exact = int(cfg.debug_exact)
         L.check(self.lib.occl_config_resolve(ctypes.byref(c), 1), "occl_config_resolve")
         self.c = c
         self.c_scene = L.OcclScene(self.verts.data_ptr(), self.faces.data_ptr(), vstride, fstride)

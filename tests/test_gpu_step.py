@@ -262,3 +262,39 @@ def test_tile_shapes_and_odd_image_size(oracle, cuda_lib):
         assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits)
         np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
         np.testing.assert_allclose(eng.obs[0].cpu().numpy(), ref.obs, rtol=RTOL, atol=1e-6)
+
+
+@pytest.mark.parametrize("occ", ["box", "teapot"])
+def test_fast_path_equals_exact_path_at_full_batch(cuda_lib, occ):
+    """Size-independent property at the BASELINE batch shape: the guarded fast pair evaluation takes
+    exactly the decisions of the reference-order arithmetic (debug_exact) for every pixel of every env."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    import math
+    sc = default_scene(occ)
+    N, S = 2048, 128
+    g = torch.Generator().manual_seed(0)
+    az = (math.pi / 2 - 0.6) + 1.2 * torch.rand(N, generator=g)
+    el = -0.3 + 0.6 * torch.rand(N, generator=g)
+    act = torch.randn(N, 2, generator=g).cuda()
+    res = []
+    for exact in (False, True):
+        eng = OcclusionEngine(sc, N, RasterConfig(image_size=S, debug_exact=exact), debug_outputs=True)
+        eng.reset(radius=4.0, azimuth=az, elevation=el)
+        eng.step(act, with_grad=True)
+        eng.check_status()
+        res.append(eng)
+    a, b = res
+    assert torch.equal(a.pix_to_face, b.pix_to_face)
+    assert torch.equal(a.nhits, b.nhits)
+    assert torch.equal(a.n_covered, b.n_covered) and torch.equal(a.n_visible, b.n_visible)
+    assert torch.equal(a.obs, b.obs), "observation (depth + shading) does not depend on the fast path"
+    assert torch.equal(a.done, b.done)
+    torch.testing.assert_close(a.alphas, b.alphas, rtol=RTOL, atol=ATOL_A)
+    torch.testing.assert_close(a.loss, b.loss, rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(a.reward, b.reward, rtol=RTOL, atol=2e-6)
+    ga, gb = a.grad_action, b.grad_action
+    # 1e-3 relative to the env's gradient, with an absolute floor for envs whose overlap (and gradient) is ~0:
+    # the per-pixel tangent sums are fp32 atomics whose order differs from run to run
+    scale = gb.abs().max(dim=1, keepdim=True).values
+    assert bool(((ga - gb).abs() <= 1e-3 * scale + 1e-6).all())
+    assert int(a.nhits.max()) > 100  # the K=100 cut is exercised
