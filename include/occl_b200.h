@@ -116,6 +116,12 @@ int occl_abi_version(void);
 /* Human-readable text of the last CUDA error seen by this library on the calling thread. */
 const char* occl_last_cuda_error(void);
 
+/* Self-test of the rasteriser's division primitive: counts, over n_samples pseudo-random operand
+ * pairs of its guarded domain, the results that are not bit-identical to IEEE `a / b`.
+ * mismatches_dev: one device u64 (expected 0). */
+int occl_selftest_div(unsigned long long n_samples, unsigned long long seed, unsigned long long* mismatches_dev,
+                      void* stream);
+
 /* Fill tile_w/tile_h when they are 0 and validate the configuration. */
 int occl_config_resolve(OcclConfig* cfg, int with_grad);
 

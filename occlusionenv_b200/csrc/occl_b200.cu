@@ -31,6 +31,7 @@
 #define BIG_FACE_PX 192       // faces covering more tile pixels than this are rasterised by the whole CTA
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
 #define DEFER_CAP 2048        // queued inside hits (exact depth resolved in a dense pass)
+#define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
 #define REC_WORDS 16
 
@@ -250,6 +251,7 @@ struct RasterParams {
   uint4* geo;    // [N][F][4]  16 words per live face, see REC_* below
   uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16)
   int* n_live;   // [N]
+  const uint32_t* tile_mask;  // [N][TILE_MASK_WORDS]
   // outputs
   float* obs;
   float* occl;
@@ -264,11 +266,14 @@ struct RasterParams {
 // Record of a live face (16 words). Words 0..9 and 12..14 are floats.
 //   0..8  x0 y0 z0 x1 y1 z1 x2 y2 z2     (x_ndc, y_ndc, z_view)
 //   9     area = (float)((double)EdgeFunction(v2,v0,v1) + kEpsilon)
-//   10    packed face index | FAST flag in bit 31
+//   10    packed face index (bits 0..27) | object id (bits 28..29) | FAST flag (bit 31)
 //   11    (tile list only) hard pixel range, tile-local, 8 bits each: x0 x1 y0 y1
 //   12..14  1/l2 of the edges v0v1, v0v2, v1v2  (fast path only)
 //   15    (tile list only) soft pixel range, tile-local, 8 bits each
 #define REC_FAST 0x80000000u
+#define REC_FIDX_MASK 0x0fffffffu
+#define REC_OBJ_SHIFT 28
+#define GROUP_LANES 8         // lanes that rasterise one small face; a warp works on 32/GROUP_LANES faces at once
 
 struct FaceGeo {
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
@@ -339,6 +344,18 @@ __device__ __noinline__ PairResult eval_pair(const FaceGeo& g, float px, float p
   return r;
 }
 
+// IEEE-754 round-to-nearest quotient a / b from y = RN(1/b) (hoisted: b is a per-face constant).
+// Two Markstein steps: q <- RN(q + RN(a - q b) y); each remainder is exact (FMA) once q is within an ulp,
+// and the second step then rounds correctly.  Requires normal-range operands and quotient, which the
+// caller guards (b in [1e-8, 128], |a| in [2^-80, 2^10]); checked against `/` by occl_selftest_div.
+__device__ __forceinline__ float div_rn_hoisted(float a, float b, float y) {
+  float q = a * y;
+  float r = __fmaf_rn(-q, b, a);
+  q = __fmaf_rn(r, y, q);
+  r = __fmaf_rn(-q, b, a);
+  return __fmaf_rn(r, y, q);
+}
+
 // clipped-barycentric depth used to order the K nearest soft hits (BarycentricClipForward)
 __device__ __forceinline__ float pz_clipped(const FaceGeo& g, float b0, float b1, float b2) {
   float c0 = b0 > 0.f ? b0 : 0.f, c1 = b1 > 0.f ? b1 : 0.f, c2 = b2 > 0.f ? b2 : 0.f;
@@ -400,7 +417,9 @@ __device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const f
 // kernel 2: per-env face setup + ordered compaction of the live faces
 // ----------------------------------------------------------------------------------------------
 struct SetupParams {
-  int S, V, F, cull;
+  int S, V, F, cull, n_obj;
+  int obj_face_start[OCCL_MAX_OBJ + 1];
+  int tile_w, tile_h, tiles_x, n_tiles;
   float bbox_r;
   const float4* vproj;
   const int* faces;
@@ -408,6 +427,7 @@ struct SetupParams {
   uint4* geo;
   uint4* rng;
   int* n_live;
+  uint32_t* tile_mask;  // [N][TILE_MASK_WORDS] bit t set: some live face's blur box overlaps tile t
   const uint8_t* env_mask;
 };
 
@@ -416,11 +436,13 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
   __shared__ int s_wcnt[OCCL_WARPS];
   __shared__ int s_base;
+  __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
   const int env = blockIdx.x;
   if (p.env_mask && !p.env_mask[env]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S;
   for (int i = tid; i < S; i += OCCL_THREADS) tab[i] = pix_to_ndc(S - 1 - i, S);
+  if (tid < TILE_MASK_WORDS) s_tmask[tid] = 0u;
   if (tid == 0) s_base = 0;
   __syncthreads();
   const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
@@ -473,7 +495,20 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
       uint4 q0, q1, q2, q3;
       q0 = make_uint4(__float_as_uint(g.x0), __float_as_uint(g.y0), __float_as_uint(g.z0), __float_as_uint(g.x1));
       q1 = make_uint4(__float_as_uint(g.y1), __float_as_uint(g.z1), __float_as_uint(g.x2), __float_as_uint(g.y2));
-      q2 = make_uint4(__float_as_uint(g.z2), __float_as_uint(g.area), (uint32_t)f | (fast ? REC_FAST : 0u), 0u);
+      uint32_t obj = 0;
+#pragma unroll
+      for (int i = 1; i < OCCL_MAX_OBJ; ++i)
+        if (i < p.n_obj && f >= p.obj_face_start[i]) obj = i;
+      q2 = make_uint4(__float_as_uint(g.z2), __float_as_uint(g.area),
+                      (uint32_t)f | (obj << REC_OBJ_SHIFT) | (fast ? REC_FAST : 0u), 0u);
+      if (p.n_tiles <= 32 * TILE_MASK_WORDS) {
+        const int tx_lo = sx0 / p.tile_w, tx_hi = sx1 / p.tile_w, ty_lo = sy0 / p.tile_h, ty_hi = sy1 / p.tile_h;
+        for (int ty = ty_lo; ty <= ty_hi; ++ty)
+          for (int tx = tx_lo; tx <= tx_hi; ++tx) {
+            const int t = ty * p.tiles_x + tx;
+            atomicOr(&s_tmask[t >> 5], 1u << (t & 31));
+          }
+      }
       q3 = make_uint4(__float_as_uint(1.0f / l01), __float_as_uint(1.0f / l02), __float_as_uint(1.0f / l12), 0u);
       uint4* o = geo + (size_t)slot * 4;
       o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
@@ -485,6 +520,7 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
     __syncthreads();
   }
   if (tid == 0) p.n_live[env] = s_base;
+  if (tid < TILE_MASK_WORDS) p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = s_tmask[tid];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -542,30 +578,33 @@ __device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g
   }
 }
 
-// One face against the pixels of its (tile-clipped) blur box; `nlanes` threads stride over them.
+// One face against the pixels of its (tile-clipped) blur box; `nlanes` threads stride over them
+// (GROUP_LANES lanes of a warp for a small face -- the other groups of the warp work on other faces in
+// the same instruction stream -- or the whole CTA for a big face).  `active` = this group has a face.
 // DEFER: inside hits are queued for a dense exact-depth pass instead of being resolved in the
 // divergent loop.
 template <bool GRAD, bool DEFER>
 __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, int tpx,
                                                    const uint32_t* __restrict__ rec, int slot_id, int env,
-                                                   int lane, int nlanes) {
+                                                   int lane, int nlanes, bool active) {
   FaceGeo g;
   load_geo(rec, &g);
   const uint32_t w10 = rec[10];
-  const int fidx = (int)(w10 & 0x7fffffffu);
+  const int fidx = (int)(w10 & REC_FIDX_MASK);
+  const int obj = (int)((w10 >> REC_OBJ_SHIFT) & 3u);
   const bool fast_face = (w10 & REC_FAST) != 0u && !p.exact_only;
   const uint32_t sb = rec[15], hb = rec[11];
   const int lx0 = sb & 0xff, lx1 = (sb >> 8) & 0xff, ly0 = (sb >> 16) & 0xff, ly1 = (sb >> 24) & 0xff;
   const int hx0 = hb & 0xff, hx1 = (hb >> 8) & 0xff, hy0 = (hb >> 16) & 0xff, hy1 = (hb >> 24) & 0xff;
-  const int obj = obj_of_face(p, fidx);
   const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
-  const int n = w * h;
-  const float inv_w = 1.0f / (float)w;
+  const int n = active ? w * h : 0;
+  const float inv_w = __fdividef(1.0f, (float)w);
   // per-face uniforms of the fast path
   const float bx01 = g.x1 - g.x0, by01 = g.y1 - g.y0;
   const float bx02 = g.x2 - g.x0, by02 = g.y2 - g.y0;
   const float bx12 = g.x2 - g.x1, by12 = g.y2 - g.y1;
   const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
+  const float y01 = __uint_as_float(rec[12]), y02 = __uint_as_float(rec[13]), y12 = __uint_as_float(rec[14]);  // RN(1/l2)
   float4 ta, tb, tc;
   if (GRAD) {
     const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
@@ -598,9 +637,13 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       // squared distances to the three edges in the reference's operation order (bit-identical to
       // seg_dist for non-degenerate edges, which the FAST flag guarantees): sigmoid(-d/sigma) has slope
       // 1/sigma = 1e4, so even a 1-ulp change of a projected point would move alpha by > 1e-5 relative
-      const float t01 = fminf(fmaxf((bx01 * dx0 + by01 * dy0) / l01, 0.0f), 1.0f);
-      const float t02 = fminf(fmaxf((bx02 * dx0 + by02 * dy0) / l02, 0.0f), 1.0f);
-      const float t12 = fminf(fmaxf((bx12 * dx1 + by12 * dy1) / l12, 0.0f), 1.0f);
+      const float n01 = bx01 * dx0 + by01 * dy0, n02 = bx02 * dx0 + by02 * dy0, n12 = bx12 * dx1 + by12 * dy1;
+      const float nmin = fminf(fminf(fabsf(n01), fabsf(n02)), fabsf(n12));
+      const float nmax = fmaxf(fmaxf(fabsf(n01), fabsf(n02)), fabsf(n12));
+      const bool div_ok = nmin >= 8.271806e-25f /*2^-80*/ && nmax <= 1024.f;  // div_rn_hoisted's domain
+      const float t01 = fminf(fmaxf(div_rn_hoisted(n01, l01, y01), 0.0f), 1.0f);
+      const float t02 = fminf(fmaxf(div_rn_hoisted(n02, l02, y02), 0.0f), 1.0f);
+      const float t12 = fminf(fmaxf(div_rn_hoisted(n12, l12, y12), 0.0f), 1.0f);
       const float ux01 = px - (g.x0 + t01 * bx01), uy01 = py - (g.y0 + t01 * by01);
       const float ux02 = px - (g.x0 + t02 * bx02), uy02 = py - (g.y0 + t02 * by02);
       const float ux12 = px - (g.x1 + t12 * bx12), uy12 = py - (g.y1 + t12 * by12);
@@ -611,8 +654,8 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       if (d01 <= d02 && d01 <= d12) { edge = 0; tt = t01; }
       else if (d02 <= d12) { edge = 1; tt = t02; }
       else { edge = 2; tt = t12; }
-      // only the inside test is shortcut (signs of the edge functions instead of six divisions)
-      need_exact = !sign_ok;
+      // shortcuts taken: inside test by signs (no six divisions), divisions by hoisted reciprocal
+      need_exact = !(sign_ok && div_ok);
     }
     if (need_exact) {
       const PairResult r = eval_pair(g, px, py);
@@ -625,7 +668,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
     const float sd = inside ? -dist : dist;
     float prob;
     if (need_exact) prob = soft_prob(sd, p.sigma);
-    else prob = __frcp_rn(1.0f + __expf(sd * p.inv_sigma));  // sigmoid(-sd/sigma)
+    else prob = __fdividef(1.0f, 1.0f + __expf(sd * p.inv_sigma));  // sigmoid(-sd/sigma), ~2 ulp
     const bool hard_ok = inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
     soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
     if (hard_ok) {
@@ -704,6 +747,37 @@ raster_kernel(const RasterParams p) {
     sm.defer_n = &s_defer_n;
   }
 
+  // ---- tiles no live face touches: background only ---------------------------------------------
+  if (n_tiles <= 32 * TILE_MASK_WORDS &&
+      !((__ldg(p.tile_mask + (size_t)env * TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u)) {
+    const size_t npix = (size_t)S * S;
+    for (int i = tid; i < tpx; i += OCCL_THREADS) {
+      const int ly = i / p.tile_w, lx = i - ly * p.tile_w;
+      const int xi = tx0 + lx, yi = ty0 + ly;
+      if (xi >= S || yi >= S) continue;
+      const size_t pix = (size_t)yi * S + xi;
+      p.occl[(size_t)env * npix + pix] = 0.f;
+      float* o = p.obs + (size_t)env * 4 * npix + pix;
+      o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
+      for (int ob = 0; ob < p.n_obj; ++ob) {
+        if (p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
+        if (p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
+      }
+      if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
+      if (p.bary) {
+        float* bq = p.bary + ((size_t)env * npix + pix) * 3;
+        bq[0] = -1.f; bq[1] = -1.f; bq[2] = -1.f;
+      }
+    }
+    if (tid == 0) {
+      Partial out;
+      out.loss = 0; out.objsq = 0; out.gl[0] = 0; out.gl[1] = 0;
+      for (int o = 0; o < OCCL_MAX_OBJ; ++o) { out.ncov[o] = 0; out.nvis[o] = 0; }
+      p.partials[(size_t)env * n_tiles + tile] = out;
+    }
+    return;
+  }
+
   // ---- init accumulators -------------------------------------------------------------------
   for (int i = tid; i < tpx; i += OCCL_THREADS) sm.hard[i] = ~0ull;
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = (unsigned long long)__float_as_uint(1.0f);
@@ -756,17 +830,19 @@ raster_kernel(const RasterParams p) {
     const int n = s_list_n;
     __syncthreads();  // everyone has read the count before the next round may append
     if (n > LIST_CAP - SCAN_CHUNK || last) {
-      // small faces: one warp per face, dynamically scheduled
+      // small faces: GROUP_LANES lanes per face, 32/GROUP_LANES faces per warp pass, dynamically scheduled
       for (;;) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(&s_next, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n) break;
-        const uint32_t* rec = sm.list + i * REC_WORDS;
+        int i0 = 0;
+        if (lane == 0) i0 = atomicAdd(&s_next, 32 / GROUP_LANES);
+        i0 = __shfl_sync(0xffffffffu, i0, 0);
+        if (i0 >= n) break;
+        const int gi = i0 + lane / GROUP_LANES;
+        bool active = gi < n;
+        const uint32_t* rec = sm.list + (active ? gi : i0) * REC_WORDS;
         const uint32_t sb = rec[15];
         const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-        if (npx > BIG_FACE_PX) continue;
-        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, i, env, lane, 32);
+        active = active && npx <= BIG_FACE_PX;
+        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, gi, env, lane % GROUP_LANES, GROUP_LANES, active);
       }
       __syncthreads();
       // dense exact-depth pass over the queued inside hits
@@ -778,12 +854,12 @@ raster_kernel(const RasterParams p) {
         FaceGeo g;
         load_geo(rec, &g);
         const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
-        hard_update(sm, g, (int)(rec[10] & 0x7fffffffu), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
+        hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
       }
       // big faces: the whole CTA on one face at a time
       const int nb = s_big_n;
       for (int b = 0; b < nb; ++b)
-        raster_face_pixels<GRAD, false>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, s_big[b], env, tid, OCCL_THREADS);
+        raster_face_pixels<GRAD, false>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, s_big[b], env, tid, OCCL_THREADS, true);
       __syncthreads();
       if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_defer_n = 0; }
       __syncthreads();
@@ -832,8 +908,8 @@ raster_kernel(const RasterParams p) {
         if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
         const uint4* __restrict__ src = geo + (size_t)k * 4;
         const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-        const int f = (int)(q2.z & 0x7fffffffu);
-        if (f < p.obj_face_start[obj] || f >= p.obj_face_start[obj + 1]) continue;
+        const int f = (int)(q2.z & REC_FIDX_MASK);
+        if ((int)((q2.z >> REC_OBJ_SHIFT) & 3u) != obj) continue;
         FaceGeo g;
         g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
         g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
@@ -924,6 +1000,29 @@ raster_kernel(const RasterParams p) {
     const int xi = tx0 + lx, yi = ty0 + ly;
     if (xi >= S || yi >= S) continue;
     const size_t pix = (size_t)yi * S + xi;
+    const unsigned long long key = sm.hard[i];
+    {
+      // untouched pixel (the common case): background, nothing to blend or reduce
+      unsigned touched = 0u;
+#pragma unroll
+      for (int o = 0; o < OCCL_MAX_OBJ; ++o)
+        if (o < p.n_obj) touched |= (unsigned)(sm.soft[(size_t)o * tpx + i] >> 32);
+      if (touched == 0u && key == ~0ull) {
+        p.occl[(size_t)env * npix + pix] = 0.f;
+        float* o = p.obs + (size_t)env * 4 * npix + pix;
+        o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
+        for (int ob = 0; ob < p.n_obj; ++ob) {
+          if (p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
+          if (p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
+        }
+        if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
+        if (p.bary) {
+          float* bq = p.bary + ((size_t)env * npix + pix) * 3;
+          bq[0] = -1.f; bq[1] = -1.f; bq[2] = -1.f;
+        }
+        continue;
+      }
+    }
     float A[OCCL_MAX_OBJ], PR[OCCL_MAX_OBJ];
 #pragma unroll
     for (int o = 0; o < OCCL_MAX_OBJ; ++o) {
@@ -966,7 +1065,6 @@ raster_kernel(const RasterParams p) {
       acc_g1 += 2.0 * (double)occl * (double)g1;
     }
     // observation: nearest scene face, flat shading, background (1,1,1), depth channel
-    const unsigned long long key = sm.hard[i];
     float rgb = 1.0f, depth = -1.0f;
     int pf = -1;
     float b0 = -1.f, b1 = -1.f, b2 = -1.f;
@@ -1130,7 +1228,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, total;
   int n_tiles;
 };
 
@@ -1140,6 +1238,37 @@ static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
   b += 4 * (size_t)(c->tile_w + c->tile_h);
   return b;
+}
+
+__global__ void selftest_div_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    // splitmix64 -> two floats: b in [1e-8, 128], |a| in [2^-80, 2^10], random mantissas
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const unsigned ma = (unsigned)z & 0x7fffffu, mb = (unsigned)(z >> 23) & 0x7fffffu;
+    const unsigned ea = 127u - 80u + (unsigned)((z >> 46) % 91u);        // 2^-80 .. 2^10
+    const unsigned eb = 127u - 27u + (unsigned)((z >> 54) % 34u);        // 2^-27 .. 2^6
+    float a = __uint_as_float((ea << 23) | ma), b = __uint_as_float((eb << 23) | mb);
+    if (z >> 63) a = -a;
+    b = fminf(fmaxf(b, 1.0000001e-8f), 128.f);
+    const float y = 1.0f / b;
+    if (__float_as_uint(div_rn_hoisted(a, b, y)) != __float_as_uint(a / b)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int occl_selftest_div(unsigned long long n_samples, unsigned long long seed, unsigned long long* mismatches_dev,
+                                 void* stream) {
+  if (!mismatches_dev) return OCCL_E_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(mismatches_dev, 0, sizeof(unsigned long long), s) != cudaSuccess) return OCCL_E_CUDA;
+  selftest_div_kernel<<<148 * 8, 256, 0, s>>>(n_samples, seed, mismatches_dev);
+  if (cudaGetLastError() != cudaSuccess) return OCCL_E_CUDA;
+  return OCCL_OK;
 }
 
 extern "C" int occl_abi_version(void) { return OCCL_ABI_VERSION; }
@@ -1179,6 +1308,7 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->geo = off;      off = align_up(off + sizeof(uint4) * 4 * (size_t)n * c->n_faces, 256);
   L->rng = off;      off = align_up(off + sizeof(uint4) * (size_t)n * c->n_faces, 256);
   L->n_live = off;   off = align_up(off + sizeof(int) * (size_t)n, 256);
+  L->tile_mask = off; off = align_up(off + sizeof(uint32_t) * TILE_MASK_WORDS * (size_t)n, 256);
   L->total = off;
   return 0;
 }
@@ -1281,6 +1411,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.band = 4e-5f * p.bbox_r;
   p.exact_only = c.debug_exact;
   p.geo = (uint4*)(base + L.geo); p.rng = (uint4*)(base + L.rng); p.n_live = (int*)(base + L.n_live);
+  p.tile_mask = (const uint32_t*)(base + L.tile_mask);
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
   p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
@@ -1298,6 +1429,10 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
     sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
     sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
+    sp.tile_mask = (uint32_t*)(base + L.tile_mask);
+    sp.n_obj = c.n_obj;
+    for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
+    sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
     face_setup_kernel<<<n, OCCL_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
