@@ -26,11 +26,10 @@
 
 #define OCCL_THREADS 256
 #define OCCL_WARPS (OCCL_THREADS / 32)
-#define LIST_CAP 384          // face records staged in shared memory per round
-#define SCAN_CHUNK OCCL_THREADS
-#define BIG_FACE_PX 192       // faces covering more tile pixels than this are rasterised by the whole CTA
+#define WBUF_RECS 36          // face records staged per warp (32 new + up to 3 carried over, padded)
+#define WDEFER_CAP 256        // per-warp queue of inside hits awaiting their exact depth
+#define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by a whole warp
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
-#define DEFER_CAP 2048        // queued inside hits (exact depth resolved in a dense pass)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
 #define REC_WORDS 16
@@ -554,8 +553,8 @@ struct TileSmem {
   float* gacc;               // [n_obj][2][tpx]  (GRAD)
   float* ndc_x;              // [tile_w]
   float* ndc_y;              // [tile_h]
-  uint32_t* list;            // [LIST_CAP][REC_WORDS]  (aliased by the top-K selection buffers)
-  uint32_t* defer;           // [DEFER_CAP] inside hits of small faces awaiting their exact depth
+  uint32_t* list;            // [warps][WBUF_RECS][REC_WORDS]  (aliased by the top-K selection buffers)
+  uint32_t* defer;           // [warps][WDEFER_CAP] inside hits awaiting their exact depth
   int* defer_n;
 };
 
@@ -675,7 +674,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       bool queued = false;
       if (DEFER && !have_bary) {
         const int d = atomicAdd(sm.defer_n, 1);
-        if (d < DEFER_CAP) {
+        if (d < WDEFER_CAP) {
           sm.defer[d] = (uint32_t)pix | ((uint32_t)slot_id << 16);
           queued = true;
         }
@@ -728,8 +727,8 @@ raster_kernel(const RasterParams p) {
   const int tpx = p.tile_w * p.tile_h;
   const int S = p.S;
 
-  __shared__ int s_list_n, s_next, s_big_n, s_ovf_n, s_hit_n, s_defer_n;
-  __shared__ int s_big[LIST_CAP];
+  __shared__ int s_ovf_n, s_hit_n, s_chunk;
+  __shared__ int s_wdef_n[OCCL_WARPS];
   __shared__ int s_ovf[OVF_CAP];
   __shared__ double s_red[OCCL_WARPS][4];
   __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
@@ -739,12 +738,12 @@ raster_kernel(const RasterParams p) {
     unsigned char* q = smem_raw;
     sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
     sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
-    sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * LIST_CAP * REC_WORDS;
-    sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * DEFER_CAP;
+    sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
+    sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
     sm.gacc = (float*)q;               if (GRAD) q += sizeof(float) * 2 * tpx * p.n_obj;
     sm.ndc_x = (float*)q;              q += sizeof(float) * p.tile_w;
     sm.ndc_y = (float*)q;
-    sm.defer_n = &s_defer_n;
+    sm.defer_n = &s_wdef_n[warp];
   }
 
   // ---- tiles no live face touches: background only ---------------------------------------------
@@ -785,7 +784,8 @@ raster_kernel(const RasterParams p) {
     for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
   for (int i = tid; i < p.tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < p.tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_ovf_n = 0; s_hit_n = 0; s_defer_n = 0; }
+  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; }
+  if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
   const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
@@ -795,76 +795,97 @@ raster_kernel(const RasterParams p) {
   const int n_live = p.n_live[env];
   const int tx1 = tx0 + p.tile_w - 1, ty1 = ty0 + p.tile_h - 1;
 
-  // ---- scan the env's live faces -> tile list in shared memory (warp-ballot compaction) -> scatter ----
-  for (int base = 0; base < n_live; base += SCAN_CHUNK) {
-    const int k = base + tid;
-    bool keep = false;
-    int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
-    uint4 rg = make_uint4(0, 0, 0, 0);
-    if (k < n_live) {
-      rg = __ldg(rng + k);
-      cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
-      cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
-      keep = cx0 <= cx1 && cy0 <= cy1;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    int slot0 = 0;
-    if (lane == 0 && bal) slot0 = atomicAdd(&s_list_n, __popc(bal));
-    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-    if (keep) {
-      const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-      const uint4* __restrict__ src = geo + (size_t)k * 4;
-      uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
-      int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)(rg.z >> 16), tx1) - tx0;
-      int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)(rg.w >> 16), ty1) - ty0;
-      if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
-      q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
-      q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
-             ((uint32_t)(cy1 - ty0) << 24);
-      uint4* dst = (uint4*)(sm.list + slot * REC_WORDS);
-      dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
-      if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > BIG_FACE_PX) s_big[atomicAdd(&s_big_n, 1)] = slot;
-    }
-    __syncthreads();
-    const bool last = base + SCAN_CHUNK >= n_live;
-    const int n = s_list_n;
-    __syncthreads();  // everyone has read the count before the next round may append
-    if (n > LIST_CAP - SCAN_CHUNK || last) {
-      // small faces: GROUP_LANES lanes per face, 32/GROUP_LANES faces per warp pass, dynamically scheduled
-      for (;;) {
-        int i0 = 0;
-        if (lane == 0) i0 = atomicAdd(&s_next, 32 / GROUP_LANES);
-        i0 = __shfl_sync(0xffffffffu, i0, 0);
-        if (i0 >= n) break;
-        const int gi = i0 + lane / GROUP_LANES;
-        bool active = gi < n;
-        const uint32_t* rec = sm.list + (active ? gi : i0) * REC_WORDS;
+  // ---- every warp on its own: scan a 32-face slice of the env's live list, stage the faces whose blur box
+  // ---- overlaps the tile (ballot compaction) in the warp's buffer, scatter them, repeat.  No CTA barrier.
+  {
+    uint32_t* wbuf = sm.list + warp * (WBUF_RECS * REC_WORDS);
+    sm.defer = sm.defer + warp * WDEFER_CAP;
+    sm.defer_n = &s_wdef_n[warp];
+    int cnt = 0;  // records pending in wbuf (warp-uniform)
+    // Work unit = a "chunk" of 16 face pairs taken with stride n_chunks through the env's live list (mesh
+    // order is spatially coherent, so a strided chunk samples the whole mesh and every chunk carries about
+    // the same share of this tile's faces; a pair = 32 B of ranges = one sector).  Warps grab chunks
+    // dynamically.
+    const int n_chunks = (n_live + 31) >> 5;
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_chunk, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      const bool scanning = c < n_chunks;
+      if (scanning) {
+        const int k = 2 * (c + n_chunks * (lane >> 1)) + (lane & 1);
+        bool keep = false;
+        int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+        uint4 rg = make_uint4(0, 0, 0, 0);
+        if (k < n_live) {
+          rg = __ldg(rng + k);
+          cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
+          cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
+          keep = cx0 <= cx1 && cy0 <= cy1;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+          const uint4* __restrict__ src = geo + (size_t)k * 4;
+          uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+          int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)(rg.z >> 16), tx1) - tx0;
+          int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)(rg.w >> 16), ty1) - ty0;
+          if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
+          q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
+          q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
+                 ((uint32_t)(cy1 - ty0) << 24);
+          uint4* dst = (uint4*)(wbuf + slot * REC_WORDS);
+          dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
+        }
+        cnt += __popc(bal);
+      }
+      __syncwarp();
+      constexpr int GPW = 32 / GROUP_LANES;  // faces per warp pass
+      const int full = scanning ? (cnt / GPW) * GPW : cnt;
+      for (int j0 = 0; j0 < full; j0 += GPW) {
+        const int j = j0 + lane / GROUP_LANES;
+        const bool have = j < full;
+        const uint32_t* rec = wbuf + (have ? j : j0) * REC_WORDS;
         const uint32_t sb = rec[15];
         const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-        active = active && npx <= BIG_FACE_PX;
-        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, gi, env, lane % GROUP_LANES, GROUP_LANES, active);
+        const bool big = npx > BIG_FACE_PX;
+        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
+        // faces with many pixels: the whole warp on one face
+        const unsigned bigmask = __ballot_sync(0xffffffffu, have && big);
+        for (int gq = 0; gq < GPW; ++gq)
+          if ((bigmask >> (gq * GROUP_LANES)) & 1u)
+            raster_face_pixels<GRAD, true>(p, sm, tpx, wbuf + (j0 + gq) * REC_WORDS, j0 + gq, env, lane, 32, true);
       }
-      __syncthreads();
-      // dense exact-depth pass over the queued inside hits
-      const int nd = min(s_defer_n, DEFER_CAP);
-      for (int j = tid; j < nd; j += OCCL_THREADS) {
-        const uint32_t d = sm.defer[j];
+      __syncwarp();
+      // dense exact-depth pass over this warp's queued inside hits
+      const int nd = min(*sm.defer_n, WDEFER_CAP);
+      for (int q = lane; q < nd; q += 32) {
+        const uint32_t d = sm.defer[q];
         const int pix = (int)(d & 0xffffu);
-        const uint32_t* rec = sm.list + (d >> 16) * REC_WORDS;
+        const uint32_t* rec = wbuf + (d >> 16) * REC_WORDS;
         FaceGeo g;
         load_geo(rec, &g);
         const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
         hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
       }
-      // big faces: the whole CTA on one face at a time
-      const int nb = s_big_n;
-      for (int b = 0; b < nb; ++b)
-        raster_face_pixels<GRAD, false>(p, sm, tpx, sm.list + s_big[b] * REC_WORDS, s_big[b], env, tid, OCCL_THREADS, true);
-      __syncthreads();
-      if (tid == 0) { s_list_n = 0; s_next = 0; s_big_n = 0; s_defer_n = 0; }
-      __syncthreads();
+      __syncwarp();
+      if (lane == 0) *sm.defer_n = 0;
+      // keep the (< GPW) leftover records at the front of the buffer
+      const int rem = cnt - full;
+      if (rem > 0 && full > 0) {
+        const int nw = rem * REC_WORDS;  // <= 48 words
+        const uint32_t t0 = lane < nw ? wbuf[full * REC_WORDS + lane] : 0u;
+        const uint32_t t1 = lane + 32 < nw ? wbuf[full * REC_WORDS + lane + 32] : 0u;
+        __syncwarp();
+        if (lane < nw) wbuf[lane] = t0;
+        if (lane + 32 < nw) wbuf[lane + 32] = t1;
+      }
+      cnt = rem;
+      __syncwarp();
+      if (!scanning) break;
     }
   }
+  __syncthreads();
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
@@ -1234,7 +1255,7 @@ struct WsLayout {
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
-  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * LIST_CAP * REC_WORDS + 4 * DEFER_CAP;
+  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
   b += 4 * (size_t)(c->tile_w + c->tile_h);
   return b;
@@ -1292,7 +1313,7 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
   if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
   // the top-K selection buffers alias the face list
-  if ((size_t)HIT_CAP * (8 + 4 + 8) > (size_t)4 * LIST_CAP * REC_WORDS) return OCCL_E_INVALID;
+  if ((size_t)HIT_CAP * (8 + 4 + 8) > (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP)) return OCCL_E_INVALID;
   return OCCL_OK;
 }
 

@@ -12,9 +12,11 @@ from occlusionenv_b200.meshes import default_scene
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5  # north-star tolerance for silhouettes / depth / reward
-# alpha = 1 - prod(1 - p) is formed in fp32: its absolute resolution is the ulp of 1.0 (1.2e-7) per
-# multiply, whatever the size of alpha; allow 4 ulp(1.0) absolute on top of the relative bound.
-ATOL_A = 5e-7
+# alpha = 1 - prod_{k<=100}(1 - p_k) is formed in fp32: every factor and every multiply carries an error of
+# the order of ulp(1.0) = 1.2e-7 whatever the size of alpha (and the order of the factors is not the
+# reference's either: torch.prod vs. shared-memory accumulation), so up to ~16 ulp(1.0) absolute after 100
+# factors; the 1e-5 relative bound is what holds wherever alpha >= 0.2.
+ATOL_A = 2e-6
 
 
 def _poses(oracle, kind):

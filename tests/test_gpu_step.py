@@ -12,7 +12,7 @@ from occlusionenv_b200.meshes import default_scene, procedural_scene
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-5
-ATOL_A = 5e-7  # 4 ulp of 1.0: alpha = 1 - prod(1-p) in fp32 (see test_gpu_render_parity.py)
+ATOL_A = 2e-6  # 16 ulp of 1.0: alpha = 1 - prod_{k<=100}(1-p_k) in fp32 (see test_gpu_render_parity.py)
 
 
 def _engine(sc, n, S, **kw):
