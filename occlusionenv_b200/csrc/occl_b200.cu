@@ -26,9 +26,10 @@
 
 #define OCCL_THREADS 256
 #define OCCL_WARPS (OCCL_THREADS / 32)
-#define WBUF_RECS 36          // face records staged per warp (32 new + up to 3 carried over, padded)
+#define WBUF_RECS 64          // face records staged per warp (up to 31 pending + 32 new)
 #define WDEFER_CAP 256        // per-warp queue of inside hits awaiting their exact depth
-#define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by a whole warp
+#define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by the whole CTA
+#define BIG_CAP 32            // such faces per tile held in shared memory (more: the finding warp does them)
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
@@ -236,7 +237,7 @@ struct RasterParams {
   int S, n_obj, V, F, K, cull, exact_only;
   int obj_face_start[OCCL_MAX_OBJ + 1];
   int tile_w, tile_h, tiles_x, tiles_y;
-  float blur, bbox_r, sigma, neg_inv_sigma, inv_sigma, band;
+  float blur, bbox_r, sigma, inv_sigma, inv_sigma_log2e;
   float light[3];
   const float4* vproj;
   const float4* vtan;
@@ -341,6 +342,18 @@ __device__ __noinline__ PairResult eval_pair(const FaceGeo& g, float px, float p
     r.t = t12;
   }
   return r;
+}
+
+// raw SFU approximations (1-2 ulp): only on the tolerance path (silhouette probabilities)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // IEEE-754 round-to-nearest quotient a / b from y = RN(1/b) (hoisted: b is a per-face constant).
@@ -555,6 +568,7 @@ struct TileSmem {
   float* ndc_y;              // [tile_h]
   uint32_t* list;            // [warps][WBUF_RECS][REC_WORDS]  (aliased by the top-K selection buffers)
   uint32_t* defer;           // [warps][WDEFER_CAP] inside hits awaiting their exact depth
+  uint32_t* big;             // [BIG_CAP][REC_WORDS] faces set aside for CTA-wide rasterisation
   int* defer_n;
 };
 
@@ -667,7 +681,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
     const float sd = inside ? -dist : dist;
     float prob;
     if (need_exact) prob = soft_prob(sd, p.sigma);
-    else prob = __fdividef(1.0f, 1.0f + __expf(sd * p.inv_sigma));  // sigmoid(-sd/sigma), ~2 ulp
+    else prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
     const bool hard_ok = inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
     soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
     if (hard_ok) {
@@ -727,7 +741,7 @@ raster_kernel(const RasterParams p) {
   const int tpx = p.tile_w * p.tile_h;
   const int S = p.S;
 
-  __shared__ int s_ovf_n, s_hit_n, s_chunk;
+  __shared__ int s_ovf_n, s_hit_n, s_chunk, s_big_n;
   __shared__ int s_wdef_n[OCCL_WARPS];
   __shared__ int s_ovf[OVF_CAP];
   __shared__ double s_red[OCCL_WARPS][4];
@@ -740,6 +754,7 @@ raster_kernel(const RasterParams p) {
     sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
     sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
     sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
+    sm.big = (uint32_t*)q;             q += sizeof(uint32_t) * BIG_CAP * REC_WORDS;
     sm.gacc = (float*)q;               if (GRAD) q += sizeof(float) * 2 * tpx * p.n_obj;
     sm.ndc_x = (float*)q;              q += sizeof(float) * p.tile_w;
     sm.ndc_y = (float*)q;
@@ -784,7 +799,7 @@ raster_kernel(const RasterParams p) {
     for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
   for (int i = tid; i < p.tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < p.tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; }
+  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; }
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
@@ -841,51 +856,84 @@ raster_kernel(const RasterParams p) {
       }
       __syncwarp();
       constexpr int GPW = 32 / GROUP_LANES;  // faces per warp pass
-      const int full = scanning ? (cnt / GPW) * GPW : cnt;
-      for (int j0 = 0; j0 < full; j0 += GPW) {
-        const int j = j0 + lane / GROUP_LANES;
-        const bool have = j < full;
-        const uint32_t* rec = wbuf + (have ? j : j0) * REC_WORDS;
-        const uint32_t sb = rec[15];
-        const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-        const bool big = npx > BIG_FACE_PX;
-        raster_face_pixels<GRAD, true>(p, sm, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
-        // faces with many pixels: the whole warp on one face
-        const unsigned bigmask = __ballot_sync(0xffffffffu, have && big);
-        for (int gq = 0; gq < GPW; ++gq)
-          if ((bigmask >> (gq * GROUP_LANES)) & 1u)
-            raster_face_pixels<GRAD, true>(p, sm, tpx, wbuf + (j0 + gq) * REC_WORDS, j0 + gq, env, lane, 32, true);
-      }
-      __syncwarp();
-      // dense exact-depth pass over this warp's queued inside hits
-      const int nd = min(*sm.defer_n, WDEFER_CAP);
-      for (int q = lane; q < nd; q += 32) {
-        const uint32_t d = sm.defer[q];
-        const int pix = (int)(d & 0xffffu);
-        const uint32_t* rec = wbuf + (d >> 16) * REC_WORDS;
-        FaceGeo g;
-        load_geo(rec, &g);
-        const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
-        hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
-      }
-      __syncwarp();
-      if (lane == 0) *sm.defer_n = 0;
-      // keep the (< GPW) leftover records at the front of the buffer
-      const int rem = cnt - full;
-      if (rem > 0 && full > 0) {
-        const int nw = rem * REC_WORDS;  // <= 48 words
-        const uint32_t t0 = lane < nw ? wbuf[full * REC_WORDS + lane] : 0u;
-        const uint32_t t1 = lane + 32 < nw ? wbuf[full * REC_WORDS + lane + 32] : 0u;
+      // process batches of (up to) 32 staged faces, taken from the END of the buffer so that the
+      // leftover stays in place; the whole remainder once the scan is over
+      while (cnt >= 32 || (!scanning && cnt > 0)) {
+        const int batch = min(cnt, 32);
+        const int first = cnt - batch;
+        // sort the batch by loop trip count so that the GPW faces sharing a warp pass finish together
+        unsigned key = 0xffffffffu;
+        if (lane < batch) {
+          const uint32_t sb = wbuf[(first + lane) * REC_WORDS + 15];
+          const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
+          const unsigned trips = npx > BIG_FACE_PX ? 0u : (unsigned)((npx + GROUP_LANES - 1) / GROUP_LANES);
+          key = (trips << 8) | (unsigned)lane;  // trips == 0 marks a big face
+        }
+#pragma unroll
+        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+            const unsigned other = __shfl_xor_sync(0xffffffffu, key, j2);
+            const bool up = (lane & k2) == 0, lower = (lane & j2) == 0;
+            key = (lower == up) ? min(key, other) : max(key, other);
+          }
+        }
+        const int npass = (batch + GPW - 1) / GPW;
+        for (int pass = 0; pass < npass; ++pass) {
+          const int pos = pass * GPW + lane / GROUP_LANES;
+          const unsigned kk = __shfl_sync(0xffffffffu, key, pos);
+          const bool have = pos < batch;
+          const int j = first + (have ? (int)(kk & 0xffu) : 0);
+          const bool big = have && (kk >> 8) == 0u;
+          const uint32_t* rec = wbuf + j * REC_WORDS;
+          raster_face_pixels<GRAD, true>(p, sm, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
+          // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
+          // shared list is full the warp rasterises them itself
+          const unsigned bigmask = __ballot_sync(0xffffffffu, big);
+          if (bigmask) {
+            for (int gq = 0; gq < GPW; ++gq) {
+              const int jj = __shfl_sync(0xffffffffu, j, gq * GROUP_LANES);
+              if ((bigmask >> (gq * GROUP_LANES)) & 1u) {
+                int bslot = 0;
+                if (lane == 0) bslot = atomicAdd(&s_big_n, 1);
+                bslot = __shfl_sync(0xffffffffu, bslot, 0);
+                if (bslot < BIG_CAP) {
+                  if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
+                } else {
+                  raster_face_pixels<GRAD, true>(p, sm, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
+                }
+              }
+            }
+          }
+        }
         __syncwarp();
-        if (lane < nw) wbuf[lane] = t0;
-        if (lane + 32 < nw) wbuf[lane + 32] = t1;
+        // dense exact-depth pass over this warp's queued inside hits
+        const int nd = min(*sm.defer_n, WDEFER_CAP);
+        for (int q = lane; q < nd; q += 32) {
+          const uint32_t d = sm.defer[q];
+          const int pix = (int)(d & 0xffffu);
+          const uint32_t* rec = wbuf + (d >> 16) * REC_WORDS;
+          FaceGeo g;
+          load_geo(rec, &g);
+          const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
+          hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
+        }
+        __syncwarp();
+        if (lane == 0) *sm.defer_n = 0;
+        cnt = first;
+        __syncwarp();
       }
-      cnt = rem;
-      __syncwarp();
       if (!scanning) break;
     }
   }
   __syncthreads();
+  // ---- big faces: the whole CTA on one face at a time --------------------------------------------
+  {
+    const int nb = min(s_big_n, BIG_CAP);
+    for (int b = 0; b < nb; ++b)
+      raster_face_pixels<GRAD, false>(p, sm, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
+    if (nb) __syncthreads();
+  }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
@@ -1255,7 +1303,8 @@ struct WsLayout {
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
-  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP;
+  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP +
+             4 * BIG_CAP * REC_WORDS;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
   b += 4 * (size_t)(c->tile_w + c->tile_h);
   return b;
@@ -1427,9 +1476,8 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.tiles_x = (c.image_size + c.tile_w - 1) / c.tile_w;
   p.tiles_y = (c.image_size + c.tile_h - 1) / c.tile_h;
   p.blur = c.blur_radius; p.bbox_r = sqrtf(c.blur_radius); p.sigma = c.sigma;
-  p.inv_sigma = 1.0f / c.sigma; p.neg_inv_sigma = -p.inv_sigma;
-  // decision band of the fast path: |dist_fast - dist_reference| < ~2e-8 for |coords| <= 4
-  p.band = 4e-5f * p.bbox_r;
+  p.inv_sigma = 1.0f / c.sigma;
+  p.inv_sigma_log2e = (float)(1.4426950408889634 / (double)c.sigma);
   p.exact_only = c.debug_exact;
   p.geo = (uint4*)(base + L.geo); p.rng = (uint4*)(base + L.rng); p.n_live = (int*)(base + L.n_live);
   p.tile_mask = (const uint32_t*)(base + L.tile_mask);
