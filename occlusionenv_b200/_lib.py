@@ -61,7 +61,8 @@ EXPORTS = ["occl_abi_version", "occl_last_cuda_error", "occl_selftest_div", "occ
            "occl_finalize", "occl_step", "occl_reset", "occl_render"]
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libocclb200.so")
+# OCCL_B200_LIB: alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("OCCL_B200_LIB") or os.path.join(_PKG, "libocclb200.so")
 _lib = None
 
 

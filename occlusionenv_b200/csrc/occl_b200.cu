@@ -252,6 +252,7 @@ struct RasterParams {
   uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16)
   int* n_live;   // [N]
   const uint32_t* tile_mask;  // [N][TILE_MASK_WORDS]
+  const float2* shade;        // [N][F]
   // outputs
   float* obs;
   float* occl;
@@ -273,7 +274,9 @@ struct RasterParams {
 #define REC_FAST 0x80000000u
 #define REC_FIDX_MASK 0x0fffffffu
 #define REC_OBJ_SHIFT 28
+#ifndef GROUP_LANES
 #define GROUP_LANES 8         // lanes that rasterise one small face; a warp works on 32/GROUP_LANES faces at once
+#endif
 
 struct FaceGeo {
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
@@ -425,6 +428,47 @@ __device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const f
   return true;
 }
 
+// HardFlatShader lighting of one face: pixel independent, so it is evaluated once per live
+// face in the setup kernel.  Returns (ambient + diffuse, specular); colour = x * texel + y.
+__device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, int i0, int i1, int i2,
+                                                const float light[3], float camx, float camy, float camz) {
+  const float* w0 = wv + 3 * (size_t)i0;
+  const float* w1 = wv + 3 * (size_t)i1;
+  const float* w2 = wv + 3 * (size_t)i2;
+  float v0[3], e1[3], e2[3], ctr[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v0[k] = __ldg(w0 + k);
+    const float q1 = __ldg(w1 + k), q2 = __ldg(w2 + k);
+    e1[k] = q1 - v0[k];
+    e2[k] = q2 - v0[k];
+    ctr[k] = ((v0[k] + q1) + q2) / 3.0f;
+  }
+  float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+  float nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+  nn = nn > 1e-6f ? nn : 1e-6f;
+  n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+  nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+  nn = nn > 1e-6f ? nn : 1e-6f;
+  n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+  float dir[3] = {light[0] - ctr[0], light[1] - ctr[1], light[2] - ctr[2]};
+  float view[3] = {camx - ctr[0], camy - ctr[1], camz - ctr[2]};
+  float dn = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
+  dn = dn > 1e-6f ? dn : 1e-6f;
+  dir[0] = dir[0] / dn; dir[1] = dir[1] / dn; dir[2] = dir[2] / dn;
+  float vn = sqrtf((view[0] * view[0] + view[1] * view[1]) + view[2] * view[2]);
+  vn = vn > 1e-6f ? vn : 1e-6f;
+  view[0] = view[0] / vn; view[1] = view[1] / vn; view[2] = view[2] / vn;
+  const float cosang = (n[0] * dir[0] + n[1] * dir[1]) + n[2] * dir[2];
+  const float diffuse = 0.3f * (cosang > 0.f ? cosang : 0.f);
+  const float r0 = -dir[0] + 2.0f * (cosang * n[0]);
+  const float r1 = -dir[1] + 2.0f * (cosang * n[1]);
+  const float r2 = -dir[2] + 2.0f * (cosang * n[2]);
+  float al = (view[0] * r0 + view[1] * r1) + view[2] * r2;
+  al = (al > 0.f ? al : 0.f) * (cosang > 0.f ? 1.0f : 0.0f);
+  return make_float2(0.5f + diffuse, 0.2f * powf(al, 64.0f));
+}
+
 // ----------------------------------------------------------------------------------------------
 // kernel 2: per-env face setup + ordered compaction of the live faces
 // ----------------------------------------------------------------------------------------------
@@ -440,6 +484,11 @@ struct SetupParams {
   uint4* rng;
   int* n_live;
   uint32_t* tile_mask;  // [N][TILE_MASK_WORDS] bit t set: some live face's blur box overlaps tile t
+  float2* shade;        // [N][F] (ambient + diffuse, specular) of the live faces
+  const float* verts;
+  long long verts_stride;
+  const float* cam;
+  float light[3];
   const uint8_t* env_mask;
 };
 
@@ -524,6 +573,12 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
       q3 = make_uint4(__float_as_uint(1.0f / l01), __float_as_uint(1.0f / l02), __float_as_uint(1.0f / l12), 0u);
       uint4* o = geo + (size_t)slot * 4;
       o[0] = q0; o[1] = q1; o[2] = q2; o[3] = q3;
+      if (hx0 <= hx1) {  // only faces that can own a pixel need a colour
+        const float* __restrict__ cam = p.cam + (size_t)env * OCCL_CAM_STRIDE;
+        p.shade[(size_t)env * p.F + f] =
+            face_lighting(p.verts + (size_t)env * p.verts_stride, __ldg(faces + 3 * f + 0), __ldg(faces + 3 * f + 1),
+                          __ldg(faces + 3 * f + 2), p.light, __ldg(cam + 12), __ldg(cam + 13), __ldg(cam + 14));
+      }
       rng[slot] = make_uint4((uint32_t)sx0 | ((uint32_t)sx1 << 16), (uint32_t)sy0 | ((uint32_t)sy1 << 16),
                              (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16));
     }
@@ -752,6 +807,7 @@ raster_kernel(const RasterParams p) {
     unsigned char* q = smem_raw;
     sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
     sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
+    q = smem_raw + ((size_t)(q - smem_raw) + 15) / 16 * 16;  // records are moved as 16-byte vectors
     sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
     sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
     sm.big = (uint32_t*)q;             q += sizeof(uint32_t) * BIG_CAP * REC_WORDS;
@@ -765,6 +821,26 @@ raster_kernel(const RasterParams p) {
   if (n_tiles <= 32 * TILE_MASK_WORDS &&
       !((__ldg(p.tile_mask + (size_t)env * TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u)) {
     const size_t npix = (size_t)S * S;
+    const bool debug_out = p.alphas || p.nhits || p.pix_to_face || p.bary;
+    if (!debug_out && (p.tile_w & 3) == 0 && (S & 3) == 0) {
+      // 16-byte stores: four pixels of a row per thread and plane
+      const int qw = p.tile_w >> 2;
+      const float inv_qw = 1.0f / (float)qw;
+      const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), neg4 = make_float4(-1.f, -1.f, -1.f, -1.f),
+                   zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < qw * p.tile_h; i += OCCL_THREADS) {
+        const int ly = (int)(((float)i + 0.5f) * inv_qw), lx = (i - ly * qw) * 4;
+        const int xi = tx0 + lx, yi = ty0 + ly;
+        if (xi >= S || yi >= S) continue;
+        const size_t pix = (size_t)yi * S + xi;
+        *(float4*)(p.occl + (size_t)env * npix + pix) = zero4;
+        float* o = p.obs + (size_t)env * 4 * npix + pix;
+        *(float4*)(o) = one4;
+        *(float4*)(o + npix) = one4;
+        *(float4*)(o + 2 * npix) = one4;
+        *(float4*)(o + 3 * npix) = neg4;
+      }
+    } else
     for (int i = tid; i < tpx; i += OCCL_THREADS) {
       const int ly = i / p.tile_w, lx = i - ly * p.tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
@@ -1058,14 +1134,12 @@ raster_kernel(const RasterParams p) {
   }
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
-  const float* __restrict__ cam = p.cam + (size_t)env * OCCL_CAM_STRIDE;
-  const float* __restrict__ wv = p.verts + (size_t)env * p.verts_stride;
-  const float camx = __ldg(cam + 12), camy = __ldg(cam + 13), camz = __ldg(cam + 14);
   const size_t npix = (size_t)S * S;
   double acc_loss = 0.0, acc_obj = 0.0, acc_g0 = 0.0, acc_g1 = 0.0;
   int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
+  const float inv_tw = 1.0f / (float)p.tile_w;
   for (int i = tid; i < tpx; i += OCCL_THREADS) {
-    const int ly = i / p.tile_w, lx = i - ly * p.tile_w;
+    const int ly = (int)(((float)i + 0.5f) * inv_tw), lx = i - ly * p.tile_w;  // exact for i < 2^21
     const int xi = tx0 + lx, yi = ty0 + ly;
     if (xi >= S || yi >= S) continue;
     const size_t pix = (size_t)yi * S + xi;
@@ -1148,43 +1222,9 @@ raster_kernel(const RasterParams p) {
       const float e = (g.x2 - g.x0) * (g.y1 - g.y0) - (g.y2 - g.y0) * (g.x1 - g.x0);
       g.area = (float)((double)e + 1e-8);
       bary_persp(g, sm.ndc_x[lx], sm.ndc_y[ly], &b0, &b1, &b2);
-      const float* w0 = wv + 3 * (size_t)i0;
-      const float* w1 = wv + 3 * (size_t)i1;
-      const float* w2 = wv + 3 * (size_t)i2;
-      float v0[3], e1[3], e2[3], ctr[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        v0[k] = __ldg(w0 + k);
-        const float q1 = __ldg(w1 + k), q2 = __ldg(w2 + k);
-        e1[k] = q1 - v0[k];
-        e2[k] = q2 - v0[k];
-        ctr[k] = ((v0[k] + q1) + q2) / 3.0f;
-      }
-      float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-      float nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
-      nn = nn > 1e-6f ? nn : 1e-6f;
-      n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
-      nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
-      nn = nn > 1e-6f ? nn : 1e-6f;
-      n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
-      float dir[3] = {p.light[0] - ctr[0], p.light[1] - ctr[1], p.light[2] - ctr[2]};
-      float view[3] = {camx - ctr[0], camy - ctr[1], camz - ctr[2]};
-      float dn = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
-      dn = dn > 1e-6f ? dn : 1e-6f;
-      dir[0] = dir[0] / dn; dir[1] = dir[1] / dn; dir[2] = dir[2] / dn;
-      float vn = sqrtf((view[0] * view[0] + view[1] * view[1]) + view[2] * view[2]);
-      vn = vn > 1e-6f ? vn : 1e-6f;
-      view[0] = view[0] / vn; view[1] = view[1] / vn; view[2] = view[2] / vn;
-      const float cosang = (n[0] * dir[0] + n[1] * dir[1]) + n[2] * dir[2];
-      const float diffuse = 0.3f * (cosang > 0.f ? cosang : 0.f);
-      const float r0 = -dir[0] + 2.0f * (cosang * n[0]);
-      const float r1 = -dir[1] + 2.0f * (cosang * n[1]);
-      const float r2 = -dir[2] + 2.0f * (cosang * n[2]);
-      float al = (view[0] * r0 + view[1] * r1) + view[2] * r2;
-      al = (al > 0.f ? al : 0.f) * (cosang > 0.f ? 1.0f : 0.0f);
-      const float spec = 0.2f * powf(al, 64.0f);
+      const float2 sh = __ldg(p.shade + (size_t)env * p.F + pf);
       const float texel = (b0 + b1) + b2;
-      rgb = (0.5f + diffuse) * texel + spec;
+      rgb = sh.x * texel + sh.y;
     }
     float* o = p.obs + (size_t)env * 4 * npix + pix;
     o[0] = rgb;
@@ -1297,13 +1337,13 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, total;
   int n_tiles;
 };
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
-  size_t b = 8 * tpx + 8 * tpx * c->n_obj + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP +
+  size_t b = (8 * tpx + 8 * tpx * c->n_obj + 15) / 16 * 16 + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP +
              4 * BIG_CAP * REC_WORDS;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
   b += 4 * (size_t)(c->tile_w + c->tile_h);
@@ -1356,8 +1396,9 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (!(c->blur_radius >= 0.f) || !(c->sigma > 0.f)) return OCCL_E_INVALID;
   if (c->tile_w == 0 || c->tile_h == 0) {
     const int S = c->image_size;
-    c->tile_w = S < 64 ? S : 64;
-    c->tile_h = S < 16 ? S : 16;
+    // square tiles split the fewest faces; 32x32 px (1024 px of accumulators) keeps 3 CTAs per SM
+    c->tile_w = S < 32 ? S : 32;
+    c->tile_h = S < 32 ? S : 32;
   }
   if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
   if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
@@ -1379,6 +1420,7 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->rng = off;      off = align_up(off + sizeof(uint4) * (size_t)n * c->n_faces, 256);
   L->n_live = off;   off = align_up(off + sizeof(int) * (size_t)n, 256);
   L->tile_mask = off; off = align_up(off + sizeof(uint32_t) * TILE_MASK_WORDS * (size_t)n, 256);
+  L->shade = off;    off = align_up(off + sizeof(float2) * (size_t)n * c->n_faces, 256);
   L->total = off;
   return 0;
 }
@@ -1481,6 +1523,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.exact_only = c.debug_exact;
   p.geo = (uint4*)(base + L.geo); p.rng = (uint4*)(base + L.rng); p.n_live = (int*)(base + L.n_live);
   p.tile_mask = (const uint32_t*)(base + L.tile_mask);
+  p.shade = (const float2*)(base + L.shade);
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
   p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
@@ -1499,6 +1542,9 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
     sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
     sp.tile_mask = (uint32_t*)(base + L.tile_mask);
+    sp.shade = (float2*)(base + L.shade);
+    sp.verts = sc.verts; sp.verts_stride = sc.verts_env_stride; sp.cam = p.cam;
+    sp.light[0] = c.light[0]; sp.light[1] = c.light[1]; sp.light[2] = c.light[2];
     sp.n_obj = c.n_obj;
     for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
     sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
