@@ -182,6 +182,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("OCCL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from occlusionenv_b200.SubProcVecEnv import BatchedOcclusionVecEnv
     from occlusionenv_b200.config import RasterConfig
