@@ -26,10 +26,11 @@
 
 #define OCCL_THREADS 256
 #define OCCL_WARPS (OCCL_THREADS / 32)
-#define WBUF_RECS 64          // face records staged per warp (up to 31 pending + 32 new)
-#define WDEFER_CAP 256        // per-warp queue of inside hits awaiting their exact depth
+#define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
+#define BATCH_MIN 16          // a warp rasterises its staged faces once this many are pending
+#define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
 #define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by the whole CTA
-#define BIG_CAP 32            // such faces per tile held in shared memory (more: the finding warp does them)
+#define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
@@ -652,36 +653,36 @@ __device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g
 // DEFER: inside hits are queued for a dense exact-depth pass instead of being resolved in the
 // divergent loop.
 template <bool GRAD, bool DEFER>
-__device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, int tpx,
-                                                   const uint32_t* __restrict__ rec, int slot_id, int env,
-                                                   int lane, int nlanes, bool active) {
-  FaceGeo g;
-  load_geo(rec, &g);
+__device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, const int tile_w,
+                                                   const int tpx, const uint32_t* __restrict__ rec, int slot_id,
+                                                   int env, int lane, int nlanes, bool active) {
+  // Only what the fast path needs lives in registers across the pixel loop; the rare paths (reference-order
+  // evaluation, inline depth) reload the record from shared memory.
+  const float x0 = __uint_as_float(rec[0]), y0 = __uint_as_float(rec[1]);
+  const float x1 = __uint_as_float(rec[3]), y1 = __uint_as_float(rec[4]);
+  const float x2 = __uint_as_float(rec[6]), y2 = __uint_as_float(rec[7]);
   const uint32_t w10 = rec[10];
-  const int fidx = (int)(w10 & REC_FIDX_MASK);
-  const int obj = (int)((w10 >> REC_OBJ_SHIFT) & 3u);
   const bool fast_face = (w10 & REC_FAST) != 0u && !p.exact_only;
-  const uint32_t sb = rec[15], hb = rec[11];
-  const int lx0 = sb & 0xff, lx1 = (sb >> 8) & 0xff, ly0 = (sb >> 16) & 0xff, ly1 = (sb >> 24) & 0xff;
-  const int hx0 = hb & 0xff, hx1 = (hb >> 8) & 0xff, hy0 = (hb >> 16) & 0xff, hy1 = (hb >> 24) & 0xff;
-  const int w = lx1 - lx0 + 1, h = ly1 - ly0 + 1;
+  const uint32_t sb = rec[15];
+  const int lx0 = sb & 0xff, ly0 = (sb >> 16) & 0xff;
+  const int w = (int)((sb >> 8) & 0xff) - lx0 + 1, h = (int)((sb >> 24) & 0xff) - ly0 + 1;
   const int n = active ? w * h : 0;
   const float inv_w = __fdividef(1.0f, (float)w);
   // per-face uniforms of the fast path
-  const float bx01 = g.x1 - g.x0, by01 = g.y1 - g.y0;
-  const float bx02 = g.x2 - g.x0, by02 = g.y2 - g.y0;
-  const float bx12 = g.x2 - g.x1, by12 = g.y2 - g.y1;
+  const float bx01 = x1 - x0, by01 = y1 - y0;
+  const float bx02 = x2 - x0, by02 = y2 - y0;
+  const float bx12 = x2 - x1, by12 = y2 - y1;
   const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
   const float y01 = __uint_as_float(rec[12]), y02 = __uint_as_float(rec[13]), y12 = __uint_as_float(rec[14]);  // RN(1/l2)
   float4 ta, tb, tc;
   if (GRAD) {
     const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-    const int* __restrict__ fc = p.faces + (size_t)env * p.faces_stride + 3 * (size_t)fidx;
+    const int* __restrict__ fc = p.faces + (size_t)env * p.faces_stride + 3 * (size_t)(w10 & REC_FIDX_MASK);
     ta = __ldg(vt + __ldg(fc + 0));
     tb = __ldg(vt + __ldg(fc + 1));
     tc = __ldg(vt + __ldg(fc + 2));
   }
-  unsigned long long* soft = sm.soft + (size_t)obj * tpx;
+  unsigned long long* soft = sm.soft + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx;
   for (int i = lane; i < n; i += nlanes) {
     const int ry = (int)(((float)i + 0.5f) * inv_w);
     const int rx = i - ry * w;
@@ -692,7 +693,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
     int edge;
     bool need_exact = !fast_face;
     if (fast_face) {
-      const float dx0 = px - g.x0, dy0 = py - g.y0, dx1 = px - g.x1, dy1 = py - g.y1, dx2 = px - g.x2, dy2 = py - g.y2;
+      const float dx0 = px - x0, dy0 = py - y0, dx1 = px - x1, dy1 = py - y1, dx2 = px - x2, dy2 = py - y2;
       // edge functions in the reference's rounding (separate multiply / subtract: this TU has -fmad=false)
       const float e0 = dx1 * by12 - dy1 * bx12;
       const float e1 = dy2 * bx02 - dx2 * by02;
@@ -712,9 +713,9 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       const float t01 = fminf(fmaxf(div_rn_hoisted(n01, l01, y01), 0.0f), 1.0f);
       const float t02 = fminf(fmaxf(div_rn_hoisted(n02, l02, y02), 0.0f), 1.0f);
       const float t12 = fminf(fmaxf(div_rn_hoisted(n12, l12, y12), 0.0f), 1.0f);
-      const float ux01 = px - (g.x0 + t01 * bx01), uy01 = py - (g.y0 + t01 * by01);
-      const float ux02 = px - (g.x0 + t02 * bx02), uy02 = py - (g.y0 + t02 * by02);
-      const float ux12 = px - (g.x1 + t12 * bx12), uy12 = py - (g.y1 + t12 * by12);
+      const float ux01 = px - (x0 + t01 * bx01), uy01 = py - (y0 + t01 * by01);
+      const float ux02 = px - (x0 + t02 * bx02), uy02 = py - (y0 + t02 * by02);
+      const float ux12 = px - (x1 + t12 * bx12), uy12 = py - (y1 + t12 * by12);
       const float d01 = ux01 * ux01 + uy01 * uy01;
       const float d02 = ux02 * ux02 + uy02 * uy02;
       const float d12 = ux12 * ux12 + uy12 * uy12;
@@ -726,18 +727,25 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       need_exact = !(sign_ok && div_ok);
     }
     if (need_exact) {
+      FaceGeo g;
+      load_geo(rec, &g);
       const PairResult r = eval_pair(g, px, py);
       inside = r.inside; dist = r.dist; tt = r.t; edge = r.edge;
       b0 = r.b0; b1 = r.b1; b2 = r.b2;
       have_bary = true;
     }
     if (!inside && dist >= p.blur) continue;
-    const int pix = ly * p.tile_w + lx;
+    const int pix = ly * tile_w + lx;
     const float sd = inside ? -dist : dist;
     float prob;
     if (need_exact) prob = soft_prob(sd, p.sigma);
     else prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
-    const bool hard_ok = inside && lx >= hx0 && lx <= hx1 && ly >= hy0 && ly <= hy1;
+    bool hard_ok = false;
+    if (inside) {
+      const uint32_t hb = rec[11];
+      hard_ok = lx >= (int)(hb & 0xff) && lx <= (int)((hb >> 8) & 0xff) && ly >= (int)((hb >> 16) & 0xff) &&
+                ly <= (int)((hb >> 24) & 0xff);
+    }
     soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
     if (hard_ok) {
       bool queued = false;
@@ -748,15 +756,19 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
           queued = true;
         }
       }
-      if (!queued) hard_update(sm, g, fidx, pix, px, py, b0, b1, b2, have_bary);
+      if (!queued) {
+        FaceGeo g;
+        load_geo(rec, &g);
+        hard_update(sm, g, (int)(w10 & REC_FIDX_MASK), pix, px, py, b0, b1, b2, have_bary);
+      }
     }
     if (GRAD) {
       // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
       float ax, ay, bx, by;
       float4 da, db;
-      if (edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
-      else if (edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
-      else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+      if (edge == 0) { ax = x0; ay = y0; bx = x1; by = y1; da = ta; db = tb; }
+      else if (edge == 1) { ax = x0; ay = y0; bx = x2; by = y2; da = ta; db = tc; }
+      else { ax = x1; ay = y1; bx = x2; by = y2; da = tb; db = tc; }
       const float qx = ax + tt * (bx - ax), qy = ay + tt * (by - ay);
       const float sgn = inside ? -1.f : 1.f;
       const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
@@ -764,7 +776,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
       const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
       const float k = prob * p.inv_sigma;
-      float* ga = sm.gacc + (size_t)obj * 2 * tpx;
+      float* ga = sm.gacc + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * 2 * tpx;
       atomicAdd(ga + pix, k * dsd_el);
       atomicAdd(ga + tpx + pix, k * dsd_az);
     }
@@ -782,8 +794,10 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   return v;
 }
 
-template <bool GRAD>
-__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 2 : 3)
+// TW, TH: compile-time tile shape (0 = take it from the parameters); the fixed 32x32 instantiation turns
+// the shared-memory layout and all pixel index arithmetic into constants (register pressure!).
+template <bool GRAD, int TW, int TH>
+__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 2 : 4)
 raster_kernel(const RasterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -791,9 +805,10 @@ raster_kernel(const RasterParams p) {
   const int env = blockIdx.x / n_tiles;
   const int tile = blockIdx.x - env * n_tiles;
   if (p.env_mask && !p.env_mask[env]) return;
-  const int tx0 = (tile % p.tiles_x) * p.tile_w;
-  const int ty0 = (tile / p.tiles_x) * p.tile_h;
-  const int tpx = p.tile_w * p.tile_h;
+  const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
+  const int tx0 = (tile % p.tiles_x) * tile_w;
+  const int ty0 = (tile / p.tiles_x) * tile_h;
+  const int tpx = tile_w * tile_h;
   const int S = p.S;
 
   __shared__ int s_ovf_n, s_hit_n, s_chunk, s_big_n;
@@ -804,16 +819,16 @@ raster_kernel(const RasterParams p) {
 
   TileSmem sm;
   {
+    // fixed-size regions first so that, with a compile-time tile, every base address is a constant
     unsigned char* q = smem_raw;
-    sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
-    sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
-    q = smem_raw + ((size_t)(q - smem_raw) + 15) / 16 * 16;  // records are moved as 16-byte vectors
     sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
     sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
     sm.big = (uint32_t*)q;             q += sizeof(uint32_t) * BIG_CAP * REC_WORDS;
-    sm.gacc = (float*)q;               if (GRAD) q += sizeof(float) * 2 * tpx * p.n_obj;
-    sm.ndc_x = (float*)q;              q += sizeof(float) * p.tile_w;
-    sm.ndc_y = (float*)q;
+    sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
+    sm.ndc_x = (float*)q;              q += sizeof(float) * ((tile_w + 1) & ~1);
+    sm.ndc_y = (float*)q;              q += sizeof(float) * ((tile_h + 1) & ~1);
+    sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
+    sm.gacc = (float*)q;
     sm.defer_n = &s_wdef_n[warp];
   }
 
@@ -822,13 +837,13 @@ raster_kernel(const RasterParams p) {
       !((__ldg(p.tile_mask + (size_t)env * TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u)) {
     const size_t npix = (size_t)S * S;
     const bool debug_out = p.alphas || p.nhits || p.pix_to_face || p.bary;
-    if (!debug_out && (p.tile_w & 3) == 0 && (S & 3) == 0) {
+    if (!debug_out && (tile_w & 3) == 0 && (S & 3) == 0) {
       // 16-byte stores: four pixels of a row per thread and plane
-      const int qw = p.tile_w >> 2;
+      const int qw = tile_w >> 2;
       const float inv_qw = 1.0f / (float)qw;
       const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), neg4 = make_float4(-1.f, -1.f, -1.f, -1.f),
                    zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = tid; i < qw * p.tile_h; i += OCCL_THREADS) {
+      for (int i = tid; i < qw * tile_h; i += OCCL_THREADS) {
         const int ly = (int)(((float)i + 0.5f) * inv_qw), lx = (i - ly * qw) * 4;
         const int xi = tx0 + lx, yi = ty0 + ly;
         if (xi >= S || yi >= S) continue;
@@ -842,7 +857,7 @@ raster_kernel(const RasterParams p) {
       }
     } else
     for (int i = tid; i < tpx; i += OCCL_THREADS) {
-      const int ly = i / p.tile_w, lx = i - ly * p.tile_w;
+      const int ly = i / tile_w, lx = i - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
       if (xi >= S || yi >= S) continue;
       const size_t pix = (size_t)yi * S + xi;
@@ -873,8 +888,8 @@ raster_kernel(const RasterParams p) {
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = (unsigned long long)__float_as_uint(1.0f);
   if (GRAD)
     for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
-  for (int i = tid; i < p.tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
-  for (int i = tid; i < p.tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
+  for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
+  for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
   if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; }
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
@@ -884,7 +899,7 @@ raster_kernel(const RasterParams p) {
   const uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
   const uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
   const int n_live = p.n_live[env];
-  const int tx1 = tx0 + p.tile_w - 1, ty1 = ty0 + p.tile_h - 1;
+  const int tx1 = tx0 + tile_w - 1, ty1 = ty0 + tile_h - 1;
 
   // ---- every warp on its own: scan a 32-face slice of the env's live list, stage the faces whose blur box
   // ---- overlaps the tile (ballot compaction) in the warp's buffer, scatter them, repeat.  No CTA barrier.
@@ -934,7 +949,7 @@ raster_kernel(const RasterParams p) {
       constexpr int GPW = 32 / GROUP_LANES;  // faces per warp pass
       // process batches of (up to) 32 staged faces, taken from the END of the buffer so that the
       // leftover stays in place; the whole remainder once the scan is over
-      while (cnt >= 32 || (!scanning && cnt > 0)) {
+      while (cnt >= BATCH_MIN || (!scanning && cnt > 0)) {
         const int batch = min(cnt, 32);
         const int first = cnt - batch;
         // sort the batch by loop trip count so that the GPW faces sharing a warp pass finish together
@@ -962,7 +977,7 @@ raster_kernel(const RasterParams p) {
           const int j = first + (have ? (int)(kk & 0xffu) : 0);
           const bool big = have && (kk >> 8) == 0u;
           const uint32_t* rec = wbuf + j * REC_WORDS;
-          raster_face_pixels<GRAD, true>(p, sm, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
+          raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
           // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
           // shared list is full the warp rasterises them itself
           const unsigned bigmask = __ballot_sync(0xffffffffu, big);
@@ -976,7 +991,7 @@ raster_kernel(const RasterParams p) {
                 if (bslot < BIG_CAP) {
                   if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
                 } else {
-                  raster_face_pixels<GRAD, true>(p, sm, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
+                  raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
                 }
               }
             }
@@ -991,7 +1006,7 @@ raster_kernel(const RasterParams p) {
           const uint32_t* rec = wbuf + (d >> 16) * REC_WORDS;
           FaceGeo g;
           load_geo(rec, &g);
-          const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
+          const int ly = pix / tile_w, lx = pix - ly * tile_w;
           hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
         }
         __syncwarp();
@@ -1007,7 +1022,7 @@ raster_kernel(const RasterParams p) {
   {
     const int nb = min(s_big_n, BIG_CAP);
     for (int b = 0; b < nb; ++b)
-      raster_face_pixels<GRAD, false>(p, sm, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
+      raster_face_pixels<GRAD, false>(p, sm, tile_w, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
     if (nb) __syncthreads();
   }
 
@@ -1042,7 +1057,7 @@ raster_kernel(const RasterParams p) {
       const int slot = s_ovf[oi];
       const int obj = slot / tpx;
       const int pix = slot - obj * tpx;
-      const int ly = pix / p.tile_w, lx = pix - ly * p.tile_w;
+      const int ly = pix / tile_w, lx = pix - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
       if (tid == 0) s_hit_n = 0;
@@ -1137,9 +1152,9 @@ raster_kernel(const RasterParams p) {
   const size_t npix = (size_t)S * S;
   double acc_loss = 0.0, acc_obj = 0.0, acc_g0 = 0.0, acc_g1 = 0.0;
   int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
-  const float inv_tw = 1.0f / (float)p.tile_w;
+  const float inv_tw = 1.0f / (float)tile_w;
   for (int i = tid; i < tpx; i += OCCL_THREADS) {
-    const int ly = (int)(((float)i + 0.5f) * inv_tw), lx = i - ly * p.tile_w;  // exact for i < 2^21
+    const int ly = (int)(((float)i + 0.5f) * inv_tw), lx = i - ly * tile_w;  // exact for i < 2^21
     const int xi = tx0 + lx, yi = ty0 + ly;
     if (xi >= S || yi >= S) continue;
     const size_t pix = (size_t)yi * S + xi;
@@ -1343,10 +1358,9 @@ struct WsLayout {
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
-  size_t b = (8 * tpx + 8 * tpx * c->n_obj + 15) / 16 * 16 + 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP +
-             4 * BIG_CAP * REC_WORDS;
+  size_t b = 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP + 4 * BIG_CAP * REC_WORDS + 8 * tpx +
+             4 * (size_t)(((c->tile_w + 1) & ~1) + ((c->tile_h + 1) & ~1)) + 8 * tpx * c->n_obj;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
-  b += 4 * (size_t)(c->tile_w + c->tile_h);
   return b;
 }
 
@@ -1551,13 +1565,18 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     face_setup_kernel<<<n, OCCL_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
+  const bool fixed = c.tile_w == 32 && c.tile_h == 32;
+#define OCCL_LAUNCH_RASTER(G, W, H)                                                                                   \
+  do {                                                                                                                \
+    CK(cudaFuncSetAttribute(raster_kernel<G, W, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
+    raster_kernel<G, W, H><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
+  } while (0)
   if (grad) {
-    CK(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    raster_kernel<true><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (fixed) OCCL_LAUNCH_RASTER(true, 32, 32); else OCCL_LAUNCH_RASTER(true, 0, 0);
   } else {
-    CK(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    raster_kernel<false><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+    if (fixed) OCCL_LAUNCH_RASTER(false, 32, 32); else OCCL_LAUNCH_RASTER(false, 0, 0);
   }
+#undef OCCL_LAUNCH_RASTER
   CK(cudaGetLastError(), "raster_kernel");
   return OCCL_OK;
 }
