@@ -26,6 +26,10 @@
 
 #define OCCL_THREADS 256
 #define OCCL_WARPS (OCCL_THREADS / 32)
+#ifndef SETUP_THREADS
+#define SETUP_THREADS 256     // face_setup_kernel: one CTA per env (1024 measured slower: 1 CTA per SM)
+#endif
+#define SETUP_WARPS (SETUP_THREADS / 32)
 #define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
 #define BATCH_MIN 16          // a warp rasterises its staged faces once this many are pending
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
@@ -493,17 +497,17 @@ struct SetupParams {
   const uint8_t* env_mask;
 };
 
-__global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupParams p) {
+__global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
-  __shared__ int s_wcnt[OCCL_WARPS];
+  __shared__ int s_wcnt[SETUP_WARPS];
   __shared__ int s_base;
   __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
   const int env = blockIdx.x;
   if (p.env_mask && !p.env_mask[env]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S;
-  for (int i = tid; i < S; i += OCCL_THREADS) tab[i] = pix_to_ndc(S - 1 - i, S);
+  for (int i = tid; i < S; i += SETUP_THREADS) tab[i] = pix_to_ndc(S - 1 - i, S);
   if (tid < TILE_MASK_WORDS) s_tmask[tid] = 0u;
   if (tid == 0) s_base = 0;
   __syncthreads();
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
   uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
   uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
-  for (int base = 0; base < p.F; base += OCCL_THREADS) {
+  for (int base = 0; base < p.F; base += SETUP_THREADS) {
     const int f = base + tid;
     bool live = false;
     FaceGeo g;
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(OCCL_THREADS) face_setup_kernel(const SetupPar
     __syncthreads();
     int off = s_base, total = 0;
 #pragma unroll
-    for (int w = 0; w < OCCL_WARPS; ++w) {
+    for (int w = 0; w < SETUP_WARPS; ++w) {
       const int c = s_wcnt[w];
       if (w < warp) off += c;
       total += c;
@@ -1053,8 +1057,118 @@ raster_kernel(const RasterParams p) {
       }
     }
     __syncthreads();
+    // Batched pass: OVB overflowing pixels share one scan of the live list; a warp then selects the K nearest
+    // hits of "its" pixel.  A pixel with more than HSUB hits is left to the one-pixel-at-a-time pass below.
+    {
+#ifndef OCCL_OVB
+#define OCCL_OVB 6
+#endif
+      constexpr int OVB = OCCL_OVB, HSUB = 160;
+      static_assert(OVB * HSUB <= HIT_CAP, "sub-buffers must fit the selection buffer");
+      __shared__ int s_ocnt[OVB], s_oxi[OVB], s_oyi[OVB], s_oobj[OVB];
+      __shared__ float s_opx[OVB], s_opy[OVB];
+      for (int o0 = 0; OVB > 1 && o0 < n_ovf; o0 += OVB) {
+        const int nb = min(OVB, n_ovf - o0);
+        if (tid < nb) {
+          const int slot = s_ovf[o0 + tid];
+          const int obj = slot / tpx, pix = slot - obj * tpx;
+          const int ly = pix / tile_w, lx = pix - ly * tile_w;
+          s_ocnt[tid] = 0; s_oobj[tid] = obj; s_oxi[tid] = tx0 + lx; s_oyi[tid] = ty0 + ly;
+          s_opx[tid] = sm.ndc_x[lx]; s_opy[tid] = sm.ndc_y[ly];
+        }
+        __syncthreads();
+        for (int k = tid; k < n_live; k += OCCL_THREADS) {
+          const uint4 rg = __ldg(rng + k);
+          const int rx0 = (int)(rg.x & 0xffffu), rx1 = (int)(rg.x >> 16), ry0 = (int)(rg.y & 0xffffu), ry1 = (int)(rg.y >> 16);
+          if (rx1 < tx0 || rx0 > tx1 || ry1 < ty0 || ry0 > ty1) continue;
+          bool loaded = false;
+          FaceGeo g;
+          int f = 0, fobj = 0;
+          for (int j = 0; j < nb; ++j) {
+            const int xi = s_oxi[j], yi = s_oyi[j];
+            if (xi < rx0 || xi > rx1 || yi < ry0 || yi > ry1) continue;
+            if (!loaded) {
+              const uint4* __restrict__ src = geo + (size_t)k * 4;
+              const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+              f = (int)(q2.z & REC_FIDX_MASK);
+              fobj = (int)((q2.z >> REC_OBJ_SHIFT) & 3u);
+              g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+              g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+              g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+              g.area = __uint_as_float(q2.y);
+              loaded = true;
+            }
+            if (fobj != s_oobj[j]) continue;
+            const float px = s_opx[j], py = s_opy[j];
+            const PairResult r = eval_pair(g, px, py);
+            if (!r.inside && r.dist >= p.blur) continue;
+            const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+            const float sd = r.inside ? -r.dist : r.dist;
+            const float prob = soft_prob(sd, p.sigma);
+            const int hcount = atomicAdd(&s_ocnt[j], 1);
+            if (hcount < HSUB) {
+              const int h = j * HSUB + hcount;
+              hkey[h] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
+              hq[h] = 1.0f - prob;
+              if (GRAD) {
+                const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+                const float4 ta = __ldg(vt + __ldg(faces + 3 * f + 0)), tb = __ldg(vt + __ldg(faces + 3 * f + 1)),
+                             tc = __ldg(vt + __ldg(faces + 3 * f + 2));
+                float ax, ay, bx, by;
+                float4 da, db;
+                if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+                else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+                else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+                const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
+                const float sgn = r.inside ? -1.f : 1.f;
+                const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+                const float wa = 1.f - r.t, wb = r.t;
+                const float kk = prob / p.sigma;
+                hg[h] = kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+                hg[HIT_CAP + h] = kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (warp < nb) {
+          const int nh = s_ocnt[warp];
+          if (nh <= HSUB) {
+            const int hb0 = warp * HSUB;
+            float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+            for (int a = lane; a < nh; a += 32) {
+              const unsigned long long ka = hkey[hb0 + a];
+              int rank = 0;
+              for (int b = 0; b < nh; ++b) rank += hkey[hb0 + b] < ka;
+              if (rank < p.K) {
+                pr = pr * hq[hb0 + a];
+                if (GRAD) { g0 += hg[hb0 + a]; g1 += hg[HIT_CAP + hb0 + a]; }
+              }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+              if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+            }
+            if (lane == 0) {
+              const int slot = s_ovf[o0 + warp];
+              const int obj = slot / tpx, pix = slot - obj * tpx;
+              const unsigned long long old = sm.soft[slot];
+              sm.soft[slot] = (old & 0xffffffff00000000ull) | (unsigned long long)__float_as_uint(pr);
+              if (GRAD) {
+                sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
+                sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
+              }
+              s_ovf[o0 + warp] = -1;  // done
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
     for (int oi = 0; oi < n_ovf; ++oi) {
       const int slot = s_ovf[oi];
+      if (slot < 0) continue;
       const int obj = slot / tpx;
       const int pix = slot - obj * tpx;
       const int ly = pix / tile_w, lx = pix - ly * tile_w;
@@ -1562,7 +1676,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.n_obj = c.n_obj;
     for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
     sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
-    face_setup_kernel<<<n, OCCL_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    face_setup_kernel<<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
   const bool fixed = c.tile_w == 32 && c.tile_h == 32;
