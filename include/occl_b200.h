@@ -41,7 +41,7 @@ extern "C" {
 #define OCCL_ST_ZCLIP 1u       /* a vertex has z_view < z_clip: pytorch3d would clip triangles (not implemented) */
 #define OCCL_ST_KOVERFLOW 2u   /* some pixel had more than faces_per_pixel hits (handled: nearest-K rule applied) */
 #define OCCL_ST_HITCAP 4u      /* a pixel had more hits than the top-K selection buffer: alpha of that pixel is wrong */
-#define OCCL_ST_OVFCAP 8u      /* more overflowing pixels in one tile than the overflow list holds */
+#define OCCL_ST_OVFCAP 8u      /* reserved (overflowing pixels are handled in rounds; never set) */
 
 /* Raster / reward constants: a 1:1 mirror of createRenderers (environment.py:234-284) and of the
  * constants of step() (environment.py:219, 386-392). */

@@ -1031,17 +1031,20 @@ raster_kernel(const RasterParams p) {
   }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
+  // Rounds of at most OVF_CAP pixels; a resolved pixel carries bit 30 of its count word.
+  for (bool more = true; more;) {
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
-    const unsigned cnt = (unsigned)(sm.soft[i] >> 32) & 0x7fffffffu;
-    if ((int)cnt > p.K) {
+    const unsigned hi = (unsigned)(sm.soft[i] >> 32);
+    if ((int)(hi & 0x3fffffffu) > p.K && !(hi & 0x40000000u)) {
       const int s = atomicAdd(&s_ovf_n, 1);
       if (s < OVF_CAP) s_ovf[s] = i;
     }
   }
   __syncthreads();
   int n_ovf = s_ovf_n;
+  more = n_ovf > OVF_CAP;
   if (n_ovf > 0) {
-    if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW | (n_ovf > OVF_CAP ? OCCL_ST_OVFCAP : 0u));
+    if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
     n_ovf = min(n_ovf, OVF_CAP);
     // selection buffers alias the (now idle) face list
     unsigned long long* hkey = (unsigned long long*)sm.list;            // [HIT_CAP]
@@ -1154,7 +1157,7 @@ raster_kernel(const RasterParams p) {
               const int slot = s_ovf[o0 + warp];
               const int obj = slot / tpx, pix = slot - obj * tpx;
               const unsigned long long old = sm.soft[slot];
-              sm.soft[slot] = (old & 0xffffffff00000000ull) | (unsigned long long)__float_as_uint(pr);
+              sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
               if (GRAD) {
                 sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
                 sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
@@ -1251,7 +1254,7 @@ raster_kernel(const RasterParams p) {
         }
         if (lane == 0) {
           const unsigned long long old = sm.soft[slot];
-          sm.soft[slot] = (old & 0xffffffff00000000ull) | (unsigned long long)__float_as_uint(pr);
+          sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
           if (GRAD) {
             sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
             sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
@@ -1260,6 +1263,12 @@ raster_kernel(const RasterParams p) {
       }
       __syncthreads();
     }
+  }
+  if (more) {
+    __syncthreads();
+    if (tid == 0) s_ovf_n = 0;
+    __syncthreads();
+  }
   }
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
@@ -1307,7 +1316,7 @@ raster_kernel(const RasterParams p) {
         const unsigned hi = (unsigned)(w >> 32);
         ncov[o] += (int)(hi >> 31);
         if (p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
-        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & 0x7fffffffu);
+        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & 0x3fffffffu);
       }
     }
     float occl = 0.f, objs = 0.f;
