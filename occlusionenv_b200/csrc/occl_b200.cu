@@ -620,10 +620,24 @@ __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float 
   } while (old != assumed);
 }
 
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+// both tangent sums of a pixel in one 64-bit CAS
+__device__ __forceinline__ void grad_accumulate(unsigned long long* slot, float a, float b) {
+  unsigned long long old = *slot, assumed;
+  do {
+    assumed = old;
+    const float lo = __uint_as_float((unsigned)(assumed & 0xffffffffull)) + a;
+    const float hi = __uint_as_float((unsigned)(assumed >> 32)) + b;
+    old = atomicCAS(slot, assumed, pack2f(lo, hi));
+  } while (old != assumed);
+}
+
 struct TileSmem {
   unsigned long long* hard;  // [tpx]      (z bits << 32) | packed face index ; ~0 = background
   unsigned long long* soft;  // [n_obj][tpx]
-  float* gacc;               // [n_obj][2][tpx]  (GRAD)
+  unsigned long long* gacc;  // [n_obj][tpx] two fp32 tangent sums (d/d_el low word, d/d_az high word)  (GRAD)
   float* ndc_x;              // [tile_w]
   float* ndc_y;              // [tile_h]
   uint32_t* list;            // [warps][WBUF_RECS][REC_WORDS]  (aliased by the top-K selection buffers)
@@ -780,9 +794,7 @@ __device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const 
       const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
       const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
       const float k = prob * p.inv_sigma;
-      float* ga = sm.gacc + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * 2 * tpx;
-      atomicAdd(ga + pix, k * dsd_el);
-      atomicAdd(ga + tpx + pix, k * dsd_az);
+      grad_accumulate(sm.gacc + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx + pix, k * dsd_el, k * dsd_az);
     }
   }
 }
@@ -801,7 +813,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 // TW, TH: compile-time tile shape (0 = take it from the parameters); the fixed 32x32 instantiation turns
 // the shared-memory layout and all pixel index arithmetic into constants (register pressure!).
 template <bool GRAD, int TW, int TH>
-__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 2 : 4)
+__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 3 : 4)
 raster_kernel(const RasterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -832,7 +844,7 @@ raster_kernel(const RasterParams p) {
     sm.ndc_x = (float*)q;              q += sizeof(float) * ((tile_w + 1) & ~1);
     sm.ndc_y = (float*)q;              q += sizeof(float) * ((tile_h + 1) & ~1);
     sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
-    sm.gacc = (float*)q;
+    sm.gacc = (unsigned long long*)q;
     sm.defer_n = &s_wdef_n[warp];
   }
 
@@ -891,7 +903,7 @@ raster_kernel(const RasterParams p) {
   for (int i = tid; i < tpx; i += OCCL_THREADS) sm.hard[i] = ~0ull;
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = (unsigned long long)__float_as_uint(1.0f);
   if (GRAD)
-    for (int i = tid; i < 2 * tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0.f;
+    for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
   if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; }
@@ -1159,8 +1171,7 @@ raster_kernel(const RasterParams p) {
               const unsigned long long old = sm.soft[slot];
               sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
               if (GRAD) {
-                sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
-                sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
+                sm.gacc[(size_t)obj * tpx + pix] = pack2f(g0, g1);
               }
               s_ovf[o0 + warp] = -1;  // done
             }
@@ -1256,8 +1267,7 @@ raster_kernel(const RasterParams p) {
           const unsigned long long old = sm.soft[slot];
           sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
           if (GRAD) {
-            sm.gacc[(size_t)obj * 2 * tpx + pix] = g0;
-            sm.gacc[(size_t)obj * 2 * tpx + tpx + pix] = g1;
+            sm.gacc[(size_t)obj * tpx + pix] = pack2f(g0, g1);
           }
         }
       }
@@ -1338,8 +1348,9 @@ raster_kernel(const RasterParams p) {
         if (o < p.n_obj) {
           const float others = objs - A[o];
           const float c = -PR[o] * others;
-          g0 += c * sm.gacc[(size_t)o * 2 * tpx + i];
-          g1 += c * sm.gacc[(size_t)o * 2 * tpx + tpx + i];
+          const unsigned long long gw = sm.gacc[(size_t)o * tpx + i];
+          g0 += c * __uint_as_float((unsigned)(gw & 0xffffffffull));
+          g1 += c * __uint_as_float((unsigned)(gw >> 32));
         }
       }
       acc_g0 += 2.0 * (double)occl * (double)g0;
