@@ -31,7 +31,12 @@
 #endif
 #define SETUP_WARPS (SETUP_THREADS / 32)
 #define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
+#ifndef BATCH_MIN
 #define BATCH_MIN 16          // a warp rasterises its staged faces once this many are pending
+#endif
+#ifndef FACES_PER_PASS
+#define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
+#endif
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
 #define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by the whole CTA
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
@@ -962,56 +967,71 @@ raster_kernel(const RasterParams p) {
         cnt += __popc(bal);
       }
       __syncwarp();
-      constexpr int GPW = 32 / GROUP_LANES;  // faces per warp pass
       // process batches of (up to) 32 staged faces, taken from the END of the buffer so that the
       // leftover stays in place; the whole remainder once the scan is over
       while (cnt >= BATCH_MIN || (!scanning && cnt > 0)) {
         const int batch = min(cnt, 32);
         const int first = cnt - batch;
-        // sort the batch by loop trip count so that the GPW faces sharing a warp pass finish together
-        unsigned key = 0xffffffffu;
+        // lane l < batch looks at face first + l: its pixel count (0 for a big face, which is set aside)
+        int npx_l = 0;
+        bool big_l = false;
         if (lane < batch) {
           const uint32_t sb = wbuf[(first + lane) * REC_WORDS + 15];
           const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-          const unsigned trips = npx > BIG_FACE_PX ? 0u : (unsigned)((npx + GROUP_LANES - 1) / GROUP_LANES);
-          key = (trips << 8) | (unsigned)lane;  // trips == 0 marks a big face
+          big_l = npx > BIG_FACE_PX;
+          npx_l = big_l ? 0 : npx;
         }
-#pragma unroll
-        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-#pragma unroll
-          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-            const unsigned other = __shfl_xor_sync(0xffffffffu, key, j2);
-            const bool up = (lane & k2) == 0, lower = (lane & j2) == 0;
-            key = (lower == up) ? min(key, other) : max(key, other);
+        // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
+        // shared list is full the warp rasterises them itself
+        unsigned bigmask = __ballot_sync(0xffffffffu, big_l);
+        while (bigmask) {
+          const int jj = first + __ffs(bigmask) - 1;
+          bigmask &= bigmask - 1;
+          int bslot = 0;
+          if (lane == 0) bslot = atomicAdd(&s_big_n, 1);
+          bslot = __shfl_sync(0xffffffffu, bslot, 0);
+          if (bslot < BIG_CAP) {
+            if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
+          } else {
+            raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
           }
         }
-        const int npass = (batch + GPW - 1) / GPW;
-        for (int pass = 0; pass < npass; ++pass) {
-          const int pos = pass * GPW + lane / GROUP_LANES;
-          const unsigned kk = __shfl_sync(0xffffffffu, key, pos);
-          const bool have = pos < batch;
-          const int j = first + (have ? (int)(kk & 0xffu) : 0);
-          const bool big = have && (kk >> 8) == 0u;
-          const uint32_t* rec = wbuf + j * REC_WORDS;
-          raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, rec, j, env, lane % GROUP_LANES, GROUP_LANES, have && !big);
-          // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
-          // shared list is full the warp rasterises them itself
-          const unsigned bigmask = __ballot_sync(0xffffffffu, big);
-          if (bigmask) {
-            for (int gq = 0; gq < GPW; ++gq) {
-              const int jj = __shfl_sync(0xffffffffu, j, gq * GROUP_LANES);
-              if ((bigmask >> (gq * GROUP_LANES)) & 1u) {
-                int bslot = 0;
-                if (lane == 0) bslot = atomicAdd(&s_big_n, 1);
-                bslot = __shfl_sync(0xffffffffu, bslot, 0);
-                if (bslot < BIG_CAP) {
-                  if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
-                } else {
-                  raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
-                }
-              }
-            }
+        // One pass = FACES_PER_PASS faces sharing the warp; the 32 lanes are dealt to them in proportion to
+        // their pixel counts, so that all faces of a pass need (almost) the same number of loop trips.
+        for (int f0 = 0; f0 < batch; f0 += FACES_PER_PASS) {
+          int c[FACES_PER_PASS + 1];  // lane boundaries: face g owns lanes [c[g], c[g+1])
+          int nsum = 0;
+          int nf[FACES_PER_PASS];
+#pragma unroll
+          for (int g = 0; g < FACES_PER_PASS; ++g) {
+            nf[g] = __shfl_sync(0xffffffffu, npx_l, (f0 + g) & 31);
+            if (f0 + g >= batch) nf[g] = 0;
+            c[g] = nsum;  // exclusive prefix for now
+            nsum += nf[g];
           }
+          if (nsum == 0) continue;
+          const float scale = __fdividef(32.0f, (float)nsum);
+          c[0] = 0;
+          c[FACES_PER_PASS] = 32;
+#pragma unroll
+          for (int g = 1; g < FACES_PER_PASS; ++g) c[g] = __float2int_rn((float)c[g] * scale);
+          // every face with pixels gets at least one lane
+#pragma unroll
+          for (int g = 1; g < FACES_PER_PASS; ++g) c[g] = max(c[g], c[g - 1] + (nf[g - 1] > 0 ? 1 : 0));
+#pragma unroll
+          for (int g = FACES_PER_PASS - 1; g >= 1; --g) c[g] = min(c[g], c[g + 1] - (nf[g] > 0 ? 1 : 0));
+          int g_mine = 0, start = 0, end = 32;
+#pragma unroll
+          for (int g = 1; g < FACES_PER_PASS; ++g) {
+            if (lane >= c[g]) { g_mine = g; start = c[g]; }
+          }
+#pragma unroll
+          for (int g = FACES_PER_PASS - 1; g >= 1; --g) {
+            if (lane < c[g]) end = c[g];
+          }
+          const int j = first + min(f0 + g_mine, batch - 1);
+          raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + j * REC_WORDS, j, env, lane - start, end - start,
+                                         f0 + g_mine < batch);
         }
         __syncwarp();
         // dense exact-depth pass over this warp's queued inside hits
