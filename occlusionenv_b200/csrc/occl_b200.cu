@@ -31,6 +31,9 @@
 #endif
 #define SETUP_WARPS (SETUP_THREADS / 32)
 #define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
+#ifndef OCCL_RFP_INLINE
+#define OCCL_RFP_INLINE __forceinline__
+#endif
 #ifndef BATCH_MIN
 #define BATCH_MIN 16          // a warp rasterises its staged faces once this many are pending
 #endif
@@ -676,7 +679,7 @@ __device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g
 // DEFER: inside hits are queued for a dense exact-depth pass instead of being resolved in the
 // divergent loop.
 template <bool GRAD, bool DEFER>
-__device__ __forceinline__ void raster_face_pixels(const RasterParams& p, const TileSmem& sm, const int tile_w,
+__device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const TileSmem& sm, const int tile_w,
                                                    const int tpx, const uint32_t* __restrict__ rec, int slot_id,
                                                    int env, int lane, int nlanes, bool active) {
   // Only what the fast path needs lives in registers across the pixel loop; the rare paths (reference-order
@@ -973,27 +976,28 @@ raster_kernel(const RasterParams p) {
         const int batch = min(cnt, 32);
         const int first = cnt - batch;
         // lane l < batch looks at face first + l: its pixel count (0 for a big face, which is set aside)
-        int npx_l = 0;
+        int npx_l = 0, npx_raw = 0;
         bool big_l = false;
         if (lane < batch) {
           const uint32_t sb = wbuf[(first + lane) * REC_WORDS + 15];
-          const int npx = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-          big_l = npx > BIG_FACE_PX;
-          npx_l = big_l ? 0 : npx;
+          npx_raw = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
+          big_l = npx_raw > BIG_FACE_PX;
+          npx_l = big_l ? 0 : npx_raw;
         }
         // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
-        // shared list is full the warp rasterises them itself
+        // shared list is full they stay in the batch (the lane allocation gives them most of the warp)
         unsigned bigmask = __ballot_sync(0xffffffffu, big_l);
         while (bigmask) {
-          const int jj = first + __ffs(bigmask) - 1;
+          const int bl = __ffs(bigmask) - 1;
+          const int jj = first + bl;
           bigmask &= bigmask - 1;
           int bslot = 0;
           if (lane == 0) bslot = atomicAdd(&s_big_n, 1);
           bslot = __shfl_sync(0xffffffffu, bslot, 0);
           if (bslot < BIG_CAP) {
             if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
-          } else {
-            raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + jj * REC_WORDS, jj, env, lane, 32, true);
+          } else if (lane == bl) {
+            npx_l = npx_raw;
           }
         }
         // One pass = FACES_PER_PASS faces sharing the warp; the 32 lanes are dealt to them in proportion to
@@ -1057,8 +1061,24 @@ raster_kernel(const RasterParams p) {
   // ---- big faces: the whole CTA on one face at a time --------------------------------------------
   {
     const int nb = min(s_big_n, BIG_CAP);
-    for (int b = 0; b < nb; ++b)
-      raster_face_pixels<GRAD, false>(p, sm, tile_w, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
+    for (int b = 0; b < nb; ++b) {
+      raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
+      __syncwarp();
+      // this warp's queued inside hits of face b
+      const int nd = min(*sm.defer_n, WDEFER_CAP);
+      for (int q = lane; q < nd; q += 32) {
+        const uint32_t d = sm.defer[q];
+        const int pix = (int)(d & 0xffffu);
+        const uint32_t* rec = sm.big + (d >> 16) * REC_WORDS;
+        FaceGeo g;
+        load_geo(rec, &g);
+        const int ly = pix / tile_w, lx = pix - ly * tile_w;
+        hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
+      }
+      __syncwarp();
+      if (lane == 0) *sm.defer_n = 0;
+      __syncwarp();
+    }
     if (nb) __syncthreads();
   }
 
