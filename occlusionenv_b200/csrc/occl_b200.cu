@@ -405,8 +405,8 @@ __device__ __forceinline__ float soft_prob(float signed_dist, float sigma) {
 __device__ __forceinline__ void ndc_range_to_pixels(const float* __restrict__ tab, float lo, float hi,
                                                     int S, int* i0, int* i1) {
   const float fS = (float)S;
-  float e0 = ceilf(((1.0f - hi) * fS - 1.0f) * 0.5f) - 1.0f;
-  float e1 = floorf(((1.0f - lo) * fS - 1.0f) * 0.5f) + 1.0f;
+  float e0 = ceilf(((1.0f - hi) * fS - 1.0f) * 0.5f);   // estimates, exact up to rounding: the loops
+  float e1 = floorf(((1.0f - lo) * fS - 1.0f) * 0.5f);  // below settle the last pixel either way
   e0 = fminf(fmaxf(e0, 0.0f), fS);
   e1 = fminf(fmaxf(e1, -1.0f), fS - 1.0f);
   int a = (int)e0, b = (int)e1;
@@ -483,12 +483,13 @@ __device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, in
 }
 
 // ----------------------------------------------------------------------------------------------
-// kernel 2: per-env face setup + ordered compaction of the live faces
+// kernel 2: per-env face setup + warp-ballot compaction of the live faces
 // ----------------------------------------------------------------------------------------------
 struct SetupParams {
   int S, V, F, cull, n_obj;
   int obj_face_start[OCCL_MAX_OBJ + 1];
   int tile_w, tile_h, tiles_x, n_tiles;
+  float inv_tile_w, inv_tile_h;
   float bbox_r;
   const float4* vproj;
   const int* faces;
@@ -508,7 +509,6 @@ struct SetupParams {
 __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
-  __shared__ int s_wcnt[SETUP_WARPS];
   __shared__ int s_base;
   __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
   const int env = blockIdx.x;
@@ -523,8 +523,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
   uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
   uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
-  for (int base = 0; base < p.F; base += SETUP_THREADS) {
-    const int f = base + tid;
+  // Warps take 32-face chunks in turn and reserve list slots with one atomic per chunk: the list is in
+  // mesh order up to the interleaving of concurrently finishing warps (nothing depends on its order).
+  for (int base = warp * 32; base < p.F; base += SETUP_THREADS) {
+    const int f = base + lane;
     bool live = false;
     FaceGeo g;
     int sx0 = 0, sx1 = -1, sy0 = 0, sy1 = -1, hx0 = 0, hx1 = -1, hy0 = 0, hy1 = -1;
@@ -545,15 +547,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) s_wcnt[warp] = __popc(bal);
-    __syncthreads();
-    int off = s_base, total = 0;
-#pragma unroll
-    for (int w = 0; w < SETUP_WARPS; ++w) {
-      const int c = s_wcnt[w];
-      if (w < warp) off += c;
-      total += c;
-    }
+    int off = 0;
+    if (lane == 0 && bal) off = atomicAdd(&s_base, __popc(bal));
+    off = __shfl_sync(0xffffffffu, off, 0);
     if (live) {
       const int slot = off + __popc(bal & ((1u << lane) - 1u));
       // fast-path guards (see eval_fast): magnitudes for which sign(b_i) == sign(e_i) provably and the
@@ -576,7 +572,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       q2 = make_uint4(__float_as_uint(g.z2), __float_as_uint(g.area),
                       (uint32_t)f | (obj << REC_OBJ_SHIFT) | (fast ? REC_FAST : 0u), 0u);
       if (p.n_tiles <= 32 * TILE_MASK_WORDS) {
-        const int tx_lo = sx0 / p.tile_w, tx_hi = sx1 / p.tile_w, ty_lo = sy0 / p.tile_h, ty_hi = sy1 / p.tile_h;
+        // exact for these small integers: (i + 0.5) / t never lands within 0.5/t of an integer
+        const int tx_lo = (int)(((float)sx0 + 0.5f) * p.inv_tile_w), tx_hi = (int)(((float)sx1 + 0.5f) * p.inv_tile_w);
+        const int ty_lo = (int)(((float)sy0 + 0.5f) * p.inv_tile_h), ty_hi = (int)(((float)sy1 + 0.5f) * p.inv_tile_h);
         for (int ty = ty_lo; ty <= ty_hi; ++ty)
           for (int tx = tx_lo; tx <= tx_hi; ++tx) {
             const int t = ty * p.tiles_x + tx;
@@ -595,10 +593,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       rng[slot] = make_uint4((uint32_t)sx0 | ((uint32_t)sx1 << 16), (uint32_t)sy0 | ((uint32_t)sy1 << 16),
                              (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16));
     }
-    __syncthreads();
-    if (tid == 0) s_base += total;
-    __syncthreads();
   }
+  __syncthreads();
   if (tid == 0) p.n_live[env] = s_base;
   if (tid < TILE_MASK_WORDS) p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = s_tmask[tid];
 }
@@ -1736,6 +1732,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.n_obj = c.n_obj;
     for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
     sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
+    sp.inv_tile_w = 1.0f / (float)c.tile_w; sp.inv_tile_h = 1.0f / (float)c.tile_h;
     face_setup_kernel<<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
