@@ -31,6 +31,12 @@
 #endif
 #define SETUP_WARPS (SETUP_THREADS / 32)
 #define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
+#ifndef OCCL_CTAS_FWD
+#define OCCL_CTAS_FWD 4       // resident CTAs per SM the forward kernel is compiled for (64 registers)
+#endif
+#ifndef OCCL_CTAS_GRAD
+#define OCCL_CTAS_GRAD 3      // ... and the differentiable kernel (80 registers)
+#endif
 #ifndef OCCL_RFP_INLINE
 #define OCCL_RFP_INLINE __forceinline__
 #endif
@@ -611,13 +617,18 @@ __device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
 }
 
 // soft accumulator word: low 32 bits = running product of (1 - prob) as float bits,
-// high 32 bits = hit count (bits 0..30) | hard-covered flag (bit 31)
+// high 32 bits = hit count (bits 0..14) | count of "weak" hits with 1 - prob > 1/4 (bits 15..29) |
+//                top-K resolved flag (bit 30) | hard-covered flag (bit 31)
+#define SOFT_CNT_MASK 0x7fffu
+#define SOFT_WEAK_SHIFT 15
+#define SOFT_RESOLVED 0x40000000u
+#define SOFT_STRONG_NEEDED 13  // 0.25^13 < 2^-25: that many strong factors make 1 - product == 1.0f exactly
 __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float q, bool covered) {
   unsigned long long old = *slot, assumed;
   do {
     assumed = old;
     const float pr = __uint_as_float((unsigned)(assumed & 0xffffffffull)) * q;
-    unsigned hi = (unsigned)(assumed >> 32) + 1u;
+    unsigned hi = (unsigned)(assumed >> 32) + (q > 0.25f ? 1u + (1u << SOFT_WEAK_SHIFT) : 1u);
     if (covered) hi |= 0x80000000u;
     const unsigned long long nw = ((unsigned long long)hi << 32) | (unsigned long long)__float_as_uint(pr);
     old = atomicCAS(slot, assumed, nw);
@@ -817,7 +828,7 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 // TW, TH: compile-time tile shape (0 = take it from the parameters); the fixed 32x32 instantiation turns
 // the shared-memory layout and all pixel index arithmetic into constants (register pressure!).
 template <bool GRAD, int TW, int TH>
-__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? 3 : 4)
+__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? OCCL_CTAS_GRAD : OCCL_CTAS_FWD)
 raster_kernel(const RasterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1083,9 +1094,19 @@ raster_kernel(const RasterParams p) {
   for (bool more = true; more;) {
   for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
     const unsigned hi = (unsigned)(sm.soft[i] >> 32);
-    if ((int)(hi & 0x3fffffffu) > p.K && !(hi & 0x40000000u)) {
-      const int s = atomicAdd(&s_ovf_n, 1);
-      if (s < OVF_CAP) s_ovf[s] = i;
+    if ((int)(hi & SOFT_CNT_MASK) > p.K && !(hi & SOFT_RESOLVED)) {
+      // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
+      // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
+      // reference's alpha is exactly 1.0f: no selection needed.
+      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_CNT_MASK);
+      if (p.K - weak >= SOFT_STRONG_NEEDED) {
+        sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
+        if (GRAD) sm.gacc[i] = 0ull;
+        atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+      } else {
+        const int s = atomicAdd(&s_ovf_n, 1);
+        if (s < OVF_CAP) s_ovf[s] = i;
+      }
     }
   }
   __syncthreads();
@@ -1205,7 +1226,7 @@ raster_kernel(const RasterParams p) {
               const int slot = s_ovf[o0 + warp];
               const int obj = slot / tpx, pix = slot - obj * tpx;
               const unsigned long long old = sm.soft[slot];
-              sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
+              sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(pr);
               if (GRAD) {
                 sm.gacc[(size_t)obj * tpx + pix] = pack2f(g0, g1);
               }
@@ -1216,6 +1237,10 @@ raster_kernel(const RasterParams p) {
         __syncthreads();
       }
     }
+    // One pixel at a time, for pixels with more hits than a batch sub-buffer holds: two scans of the live
+    // list.  Scan 1 collects only the sort keys (pz_clipped, face) -- KEY_CAP of them fit the selection
+    // buffer -- and the K-th smallest becomes the threshold; scan 2 re-evaluates the hits and multiplies
+    // those at or below the threshold.
     for (int oi = 0; oi < n_ovf; ++oi) {
       const int slot = s_ovf[oi];
       if (slot < 0) continue;
@@ -1224,30 +1249,38 @@ raster_kernel(const RasterParams p) {
       const int ly = pix / tile_w, lx = pix - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
+      constexpr int KEY_CAP = (HIT_CAP * 20) / 8;
+      __shared__ unsigned long long s_tau;
       if (tid == 0) s_hit_n = 0;
       __syncthreads();
-      // candidates: live faces of this object whose blur box holds the pixel (exact integer ranges)
-      for (int k = tid; k < n_live; k += OCCL_THREADS) {
-        const uint4 rg = __ldg(rng + k);
-        if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
-        const uint4* __restrict__ src = geo + (size_t)k * 4;
-        const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-        const int f = (int)(q2.z & REC_FIDX_MASK);
-        if ((int)((q2.z >> REC_OBJ_SHIFT) & 3u) != obj) continue;
-        FaceGeo g;
-        g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
-        g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
-        g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
-        g.area = __uint_as_float(q2.y);
-        const PairResult r = eval_pair(g, px, py);
-        if (!r.inside && r.dist >= p.blur) continue;
-        const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
-        const float sd = r.inside ? -r.dist : r.dist;
-        const float prob = soft_prob(sd, p.sigma);
-        const int h = atomicAdd(&s_hit_n, 1);
-        if (h < HIT_CAP) {
-          hkey[h] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
-          hq[h] = 1.0f - prob;
+      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+      unsigned long long tau = 0ull;
+      for (int scan = 0; scan < 2; ++scan) {
+        for (int k = tid; k < n_live; k += OCCL_THREADS) {
+          const uint4 rg = __ldg(rng + k);
+          if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
+          const uint4* __restrict__ src = geo + (size_t)k * 4;
+          const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+          const int f = (int)(q2.z & REC_FIDX_MASK);
+          if ((int)((q2.z >> REC_OBJ_SHIFT) & 3u) != obj) continue;
+          FaceGeo g;
+          g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+          g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+          g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+          g.area = __uint_as_float(q2.y);
+          const PairResult r = eval_pair(g, px, py);
+          if (!r.inside && r.dist >= p.blur) continue;
+          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+          const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
+          if (scan == 0) {
+            const int h = atomicAdd(&s_hit_n, 1);
+            if (h < KEY_CAP) hkey[h] = key;
+            continue;
+          }
+          if (key > tau) continue;
+          const float sd = r.inside ? -r.dist : r.dist;
+          const float prob = soft_prob(sd, p.sigma);
+          pr = pr * (1.0f - prob);
           if (GRAD) {
             const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
             const float4 ta = __ldg(vt + __ldg(faces + 3 * f + 0)), tb = __ldg(vt + __ldg(faces + 3 * f + 1)),
@@ -1262,50 +1295,42 @@ raster_kernel(const RasterParams p) {
             const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
             const float wa = 1.f - r.t, wb = r.t;
             const float kk = prob / p.sigma;
-            hg[h] = kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
-            hg[HIT_CAP + h] = kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+            g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+            g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
           }
         }
-      }
-      __syncthreads();
-      int nh = s_hit_n;
-      if (nh > HIT_CAP) {
-        if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
-        nh = HIT_CAP;
-      }
-      // rank of every hit by (pz, face) ; the K smallest survive. Products are taken in rank order.
-      __shared__ float s_sel_q[128];
-      __shared__ float s_sel_g[2][128];
-      const int Ksel = min(p.K, 128);
-      for (int a = tid; a < nh; a += OCCL_THREADS) {
-        const unsigned long long ka = hkey[a];
-        int rank = 0;
-        for (int b = 0; b < nh; ++b) rank += hkey[b] < ka;
-        if (rank < Ksel) {
-          s_sel_q[rank] = hq[a];
-          if (GRAD) { s_sel_g[0][rank] = hg[a]; s_sel_g[1][rank] = hg[HIT_CAP + a]; }
+        __syncthreads();
+        if (scan == 0) {
+          int nh = s_hit_n;
+          if (nh > KEY_CAP) {
+            if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
+            nh = KEY_CAP;
+          }
+          const int want = min(p.K, nh) - 1;  // rank of the last key kept
+          for (int a = tid; a < nh; a += OCCL_THREADS) {
+            const unsigned long long ka = hkey[a];
+            int rank = 0;
+            for (int b = 0; b < nh; ++b) rank += hkey[b] < ka;
+            if (rank == want) s_tau = ka;
+          }
+          __syncthreads();
+          tau = s_tau;
         }
       }
-      __syncthreads();
-      if (warp == 0) {
-        const int m = min(nh, Ksel);
-        float pr = 1.0f, g0 = 0.f, g1 = 0.f;
-        for (int a = lane; a < m; a += 32) {
-          pr = pr * s_sel_q[a];
-          if (GRAD) { g0 += s_sel_g[0][a]; g1 += s_sel_g[1][a]; }
-        }
+      // CTA product / sums of the selected hits
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
-          if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
-        }
-        if (lane == 0) {
-          const unsigned long long old = sm.soft[slot];
-          sm.soft[slot] = (old & 0xffffffff00000000ull) | (1ull << 62) | (unsigned long long)__float_as_uint(pr);
-          if (GRAD) {
-            sm.gacc[(size_t)obj * tpx + pix] = pack2f(g0, g1);
-          }
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+        if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+      }
+      if (lane == 0) { s_red[warp][0] = (double)pr; s_red[warp][1] = (double)g0; s_red[warp][2] = (double)g1; }
+      __syncthreads();
+      if (tid == 0) {
+        float P = 1.0f, G0 = 0.f, G1 = 0.f;
+        for (int w = 0; w < OCCL_WARPS; ++w) { P = P * (float)s_red[w][0]; G0 += (float)s_red[w][1]; G1 += (float)s_red[w][2]; }
+        const unsigned long long old = sm.soft[slot];
+        sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(P);
+        if (GRAD) sm.gacc[(size_t)obj * tpx + pix] = pack2f(G0, G1);
       }
       __syncthreads();
     }
@@ -1362,7 +1387,7 @@ raster_kernel(const RasterParams p) {
         const unsigned hi = (unsigned)(w >> 32);
         ncov[o] += (int)(hi >> 31);
         if (p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
-        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & 0x3fffffffu);
+        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & SOFT_CNT_MASK);
       }
     }
     float occl = 0.f, objs = 0.f;

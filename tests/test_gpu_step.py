@@ -312,22 +312,29 @@ def test_hoisted_reciprocal_division_is_ieee_exact(cuda_lib):
         assert int(bad.item()) == 0
 
 
-def test_dense_meshes_many_overflowing_pixels(oracle, cuda_lib):
+@pytest.mark.parametrize("seed,az,el", [(21, 0.5, 0.15), (4, -0.5, 0.1)])
+def test_dense_meshes_many_overflowing_pixels(oracle, cuda_lib, seed, az, el):
     """Config-3 meshes (three 20480-face objects, ShapeNet layout) at 64^2: half of the silhouette pixels
-    collect more than faces_per_pixel=100 hits (up to ~700), more than one overflow round per tile holds; the
-    nearest-K rule must still be applied to every one of them."""
+    collect more than faces_per_pixel=100 hits (700 to 1000 at the most crowded ones): every path of the
+    nearest-K rule is exercised (strong-hit shortcut, batched selection, two-scan threshold selection, several
+    overflow rounds per tile)."""
     from occlusionenv_b200.engine import OcclusionEngine
     S = 64
-    sc = procedural_scene(21, n_obj=3, subdiv=5)
+    sc = procedural_scene(seed, n_obj=3, subdiv=5)
     eng = OcclusionEngine(sc, 1, RasterConfig(image_size=S), debug_outputs=True)
-    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.15, 0.5, 4.0)
+    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), el, az, 4.0)
     Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
     eng.render(Rt, Tt, Ct)
     st = int(eng.status[0])
     assert not (st & (1 | 4)), st
     ref = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
-    assert (ref.nhits > 100).sum() > 200 and ref.nhits.max() > 500, "test scene must overflow massively"
+    assert (ref.nhits > 100).sum() > 150 and ref.nhits.max() > 500, "test scene must overflow massively"
     assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits)
     assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), ref.pix_to_face)
     np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
     np.testing.assert_allclose(float(eng.loss[0]), float(ref.loss), rtol=RTOL, atol=1e-6)
+    # differentiable variant takes the same decisions
+    eng2 = OcclusionEngine(sc, 1, RasterConfig(image_size=S, debug_exact=True), debug_outputs=True)
+    eng2.render(Rt, Tt, Ct)
+    assert torch.equal(eng.nhits, eng2.nhits) and torch.equal(eng.pix_to_face, eng2.pix_to_face)
+    torch.testing.assert_close(eng.alphas, eng2.alphas, rtol=RTOL, atol=ATOL_A)
