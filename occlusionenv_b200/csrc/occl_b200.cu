@@ -1007,42 +1007,45 @@ raster_kernel(const RasterParams p) {
             npx_l = npx_raw;
           }
         }
-        // One pass = FACES_PER_PASS faces sharing the warp; the 32 lanes are dealt to them in proportion to
-        // their pixel counts, so that all faces of a pass need (almost) the same number of loop trips.
-        for (int f0 = 0; f0 < batch; f0 += FACES_PER_PASS) {
-          int c[FACES_PER_PASS + 1];  // lane boundaries: face g owns lanes [c[g], c[g+1])
-          int nsum = 0;
-          int nf[FACES_PER_PASS];
+        // One pass = 4 consecutive faces of the batch sharing the warp; the 32 lanes are dealt to them in
+        // proportion to their pixel counts, so that all faces of a pass need (almost) the same number of loop
+        // trips.  The lane boundaries of ALL passes are computed at once: lane l works them out for face l
+        // (segmented scans over groups of 4 lanes), a pass then only fetches three of them.
+        int cstart, ptotal;
+        {
+          const int g = lane & 3;
+          int v = npx_l;
+          int t = __shfl_up_sync(0xffffffffu, v, 1);
+          if (g >= 1) v += t;
+          t = __shfl_up_sync(0xffffffffu, v, 2);
+          if (g >= 2) v += t;
+          const int total = __shfl_sync(0xffffffffu, v, lane | 3);
+          ptotal = total;
+          cstart = total > 0 ? __float2int_rn((float)(v - npx_l) * __fdividef(32.0f, (float)total)) : 0;
+          const int has = npx_l > 0 ? 1 : 0;
+          // every face with pixels gets at least one lane: forward, then backward within the group
 #pragma unroll
-          for (int g = 0; g < FACES_PER_PASS; ++g) {
-            nf[g] = __shfl_sync(0xffffffffu, npx_l, (f0 + g) & 31);
-            if (f0 + g >= batch) nf[g] = 0;
-            c[g] = nsum;  // exclusive prefix for now
-            nsum += nf[g];
-          }
-          if (nsum == 0) continue;
-          const float scale = __fdividef(32.0f, (float)nsum);
-          c[0] = 0;
-          c[FACES_PER_PASS] = 32;
-#pragma unroll
-          for (int g = 1; g < FACES_PER_PASS; ++g) c[g] = __float2int_rn((float)c[g] * scale);
-          // every face with pixels gets at least one lane
-#pragma unroll
-          for (int g = 1; g < FACES_PER_PASS; ++g) c[g] = max(c[g], c[g - 1] + (nf[g - 1] > 0 ? 1 : 0));
-#pragma unroll
-          for (int g = FACES_PER_PASS - 1; g >= 1; --g) c[g] = min(c[g], c[g + 1] - (nf[g] > 0 ? 1 : 0));
-          int g_mine = 0, start = 0, end = 32;
-#pragma unroll
-          for (int g = 1; g < FACES_PER_PASS; ++g) {
-            if (lane >= c[g]) { g_mine = g; start = c[g]; }
+          for (int sidx = 1; sidx <= 3; ++sidx) {
+            const int pc = __shfl_up_sync(0xffffffffu, cstart, 1), ph = __shfl_up_sync(0xffffffffu, has, 1);
+            if (g == sidx) cstart = max(cstart, pc + ph);
           }
 #pragma unroll
-          for (int g = FACES_PER_PASS - 1; g >= 1; --g) {
-            if (lane < c[g]) end = c[g];
+          for (int sidx = 3; sidx >= 1; --sidx) {
+            const int nc = __shfl_down_sync(0xffffffffu, cstart, 1);
+            if (g == sidx) cstart = min(cstart, (g == 3 ? 32 : nc) - has);
           }
+          if (g == 0) cstart = 0;
+        }
+        for (int f0 = 0; f0 < batch; f0 += 4) {
+          const int c1 = __shfl_sync(0xffffffffu, cstart, f0 + 1), c2 = __shfl_sync(0xffffffffu, cstart, f0 + 2),
+                    c3 = __shfl_sync(0xffffffffu, cstart, f0 + 3);
+          if (__shfl_sync(0xffffffffu, ptotal, f0) == 0) continue;  // nothing but set-aside faces in this pass
+          const int g_mine = (lane >= c1) + (lane >= c2) + (lane >= c3);
+          const int start = g_mine == 0 ? 0 : (g_mine == 1 ? c1 : (g_mine == 2 ? c2 : c3));
+          const int end = g_mine == 0 ? c1 : (g_mine == 1 ? c2 : (g_mine == 2 ? c3 : 32));
           const int j = first + min(f0 + g_mine, batch - 1);
           raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + j * REC_WORDS, j, env, lane - start, end - start,
-                                         f0 + g_mine < batch);
+                                         f0 + g_mine < batch && end > start);
         }
         __syncwarp();
         // dense exact-depth pass over this warp's queued inside hits

@@ -105,6 +105,7 @@ class OcclusionEngine:
             self.nhits = torch.empty(N, self.n_obj, S, S, dtype=torch.int32, device=dev)
         else:
             self.alphas = self.pix_to_face = self.bary = self.nhits = None
+        self._out_cache = {}
         nbytes = self.lib.occl_workspace_bytes(ctypes.byref(c), N, 1)
         if nbytes == 0:
             raise L.OcclError("occl_workspace_bytes returned 0 (invalid configuration)")
@@ -116,7 +117,14 @@ class OcclusionEngine:
         """Device pointers of the output buffers.  ``scratch=True`` routes everything except ``obs``
         and ``status`` into throw-away buffers (used by ``render()`` so that the results of the last
         transition stay intact)."""
+        key = (with_grad, None if obs is None else obs.data_ptr(), scratch)
+        cached = self._out_cache.get(key)
+        if cached is not None:
+            return cached
         o = L.OcclOutputs()
+        self._out_cache[key] = o
+        if len(self._out_cache) > 16:
+            self._out_cache.pop(next(iter(self._out_cache)))
         o.obs = (self.obs if obs is None else obs).data_ptr()
         if scratch:
             if getattr(self, "_scratch", None) is None:
@@ -216,8 +224,14 @@ class OcclusionEngine:
     def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP) -> int:
         """Host-syncing check of the per-env status words; raises on conditions the kernels flag
         instead of computing (z-clip needed, selection buffers exceeded)."""
-        bad = int((self.status & raise_on).max().item())
-        if bad:
-            raise L.OcclError(f"env status flags set: {bad:#x} (1=z-clip needed, 4=hit buffer overflow, "
-                              "8=overflow list full)")
-        return int(self.status.max().item())
+        st = self.status if self.n == 1 else self.status.max().reshape(1)  # OR of single-bit flags ~ max is enough to test
+        if self.n > 1:
+            # bitwise OR over envs
+            st = torch.bitwise_or(torch.bitwise_and(self.status, 1).max(), torch.bitwise_or(
+                torch.bitwise_and(self.status, 2).max(), torch.bitwise_or(
+                    torch.bitwise_and(self.status, 4).max(), torch.bitwise_and(self.status, 8).max()))).reshape(1)
+        val = int(st.item())
+        if val & raise_on:
+            raise L.OcclError(f"env status flags set: {val & raise_on:#x} (1=z-clip needed: a vertex is closer than "
+                              "znear/2 and pytorch3d would clip triangles, 4=more than 2560 hits on one pixel)")
+        return val
