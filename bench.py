@@ -94,7 +94,8 @@ def cpu_reference_run(occluder, S, procs, envs_per_proc, steps, warmup):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
+    procs = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = max(1, min(procs, 64))  # one process per usable host core (capped: start-up cost)
     n = args.steps + args.warmup
     est = 0.45 if args.size == 128 else 0.45 * (args.size / 128.0) ** 2  # s per env-step per core (measured)
     envs_per_proc = int(max(1, min(8, 150.0 / (n * est))))

@@ -33,6 +33,8 @@ static const double kEpsilon = 1e-8;
 /* A.1 cameras                                                                                  */
 /* ------------------------------------------------------------------------------------------ */
 
+/* torch.nn.functional.normalize as called by pytorch3d renderer/cameras.py::look_at_rotation (eps=1e-5)
+ * and renderer/lighting.py::diffuse/specular (eps=1e-6). */
 static void normalize3(const float v[3], float eps, float out[3]) {
   /* torch.nn.functional.normalize: v / max(||v||_2, eps) */
   float n = sqrtf((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
@@ -48,7 +50,9 @@ static void cross3(const float a[3], const float b[3], float o[3]) {
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-/* look_at_rotation(C, at=0, up=(0,1,0)) followed by T = -R^T C   (environment.py:367-368).
+/* pytorch3d renderer/cameras.py::look_at_rotation, called at /root/reference/environment.py:334,367 and
+ * (through look_at_view_transform) :308; followed by T = -bmm(R^T, C) of environment.py:335,368.
+ * look_at_rotation(C, at=0, up=(0,1,0)) followed by T = -R^T C   (environment.py:367-368).
  * R is row-major 3x3 with the axes as COLUMNS (R[i][0]=x[i], R[i][1]=y[i], R[i][2]=z[i]). */
 void occl_oracle_look_at(const float C[3], float R[9], float T[3]) {
   const float up[3] = {0.f, 1.f, 0.f};
@@ -106,7 +110,8 @@ void occl_oracle_pose_lookat(float dist, float elev, float azim, float C[3], flo
   occl_oracle_look_at(C, R, T);
 }
 
-/* MeshRasterizer.transform: X_view = X_world R + T; ndc.xy = s * view.xy / view.z; ndc.z := view.z. */
+/* pytorch3d renderer/mesh/rasterizer.py::MeshRasterizer.transform with FoVPerspectiveCameras defaults
+ * (environment.py:238): X_view = X_world R + T; ndc.xy = s * view.xy / view.z; ndc.z := view.z. */
 void occl_oracle_project(const float* verts, int V, const float R[9], const float T[3], float s,
                          float* out) {
   for (int v = 0; v < V; ++v) {
@@ -124,15 +129,18 @@ void occl_oracle_project(const float* verts, int V, const float R[9], const floa
 /* A.3 / A.4 naive rasteriser                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 
+/* pytorch3d csrc/rasterize_meshes/rasterization_utils.h::PixToNonSquareNdc (square image). */
 static float pix_to_ndc(int i, int S) {
   /* PixToNonSquareNdc for square images: -offset + (range*i + offset)/S, range=2, offset=1 */
   return -1.0f + (2.0f * (float)i + 1.0f) / (float)S;
 }
 
+/* pytorch3d csrc/utils/geometry_utils.h::EdgeFunctionForward(p, a, b). */
 static float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
   return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
 }
 
+/* pytorch3d csrc/utils/geometry_utils.h::PointLineDistanceForward(p, a, b) (squared distance to the segment). */
 static float point_segment_dist(float px, float py, float ax, float ay, float bx, float by,
                                 float* t_out) {
   const float bax = bx - ax, bay = by - ay;
@@ -198,7 +206,11 @@ static void setup_face(const float* fv, float bbox_r, int cull, face_t* o) {
   o->skip = skip;
 }
 
-/* One evaluation of the A.4 rule. Returns 1 and fills *h when (pixel, face) is a hit. */
+/* One evaluation of the A.4 rule = the body of the face loop of RasterizeMeshesNaiveCpu
+ * (csrc/rasterize_meshes/rasterize_meshes_cpu.cpp) / CheckPixelInsideFace (rasterize_meshes.cu), with
+ * BarycentricCoordinatesForward, BarycentricPerspectiveCorrectionForward, BarycentricClipForward and
+ * PointTriangleDistanceForward of geometry_utils.h inlined.  Settings: environment.py:249-255 (K=100, blur,
+ * cull_backfaces) and :267-273 (K=1, blur 0).  Returns 1 and fills *h when (pixel, face) is a hit. */
 static int eval_pixel_face(const face_t* fc, float px, float py, float blur_radius, int persp,
                            int clip_bary, hit_t* h) {
   if (fc->skip) return 0;
@@ -313,7 +325,8 @@ void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int 
 /* A.5 soft silhouette                                                                          */
 /* ------------------------------------------------------------------------------------------ */
 
-/* sigmoid_alpha_blend: alpha = 1 - prod_k (1 - sigmoid(-d_k/sigma) * [f_k >= 0]). */
+/* pytorch3d renderer/blending.py::sigmoid_alpha_blend as used by SoftSilhouetteShader (environment.py:263,
+ * BlendParams(sigma=1e-4) at :242): alpha = 1 - prod_k (1 - sigmoid(-d_k/sigma) * [f_k >= 0]). */
 void occl_oracle_silhouette(const int32_t* pix_to_face, const float* dists, int S, int K,
                             float sigma, float* alpha) {
   const size_t npix = (size_t)S * S;
@@ -336,7 +349,9 @@ void occl_oracle_silhouette(const int32_t* pix_to_face, const float* dists, int 
 /* A.6 hard flat shading + hard_rgb_blend + depth splice (environment.py:375-378)               */
 /* ------------------------------------------------------------------------------------------ */
 
-/* verts: world (V,3); faces: scene faces (F,3); pix_to_face/bary/zbuf from a K=1, blur=0 raster.
+/* pytorch3d renderer/mesh/shading.py::flat_shading + renderer/lighting.py (PointLights at (2,2,-2),
+ * environment.py:275) + renderer/blending.py::hard_rgb_blend + the depth splice of environment.py:376-378.
+ * verts: world (V,3); faces: scene faces (F,3); pix_to_face/bary/zbuf from a K=1, blur=0 raster.
  * obs: (4,S,S) planar = RGB + depth (-1 on background). */
 void occl_oracle_flat_shade(const float* verts, const int32_t* faces, const int32_t* pix_to_face,
                             const float* bary, const float* zbuf, int S, const float cam[3],
@@ -389,7 +404,9 @@ void occl_oracle_flat_shade(const float* verts, const int32_t* faces, const int3
 /* A.7 rasteriser backward on the silhouette route (grad of dists only)                         */
 /* ------------------------------------------------------------------------------------------ */
 
-/* grad_dists (S,S,K) -> grad_vproj (V,3) (xy only; z receives nothing on this route).          */
+/* pytorch3d csrc/rasterize_meshes/rasterize_meshes_cpu.cpp::RasterizeMeshesBackwardCpu restricted to the
+ * grad_dists input (the route of reward.backward(), demo.py:85-86): PointTriangleDistanceBackward.
+ * grad_dists (S,S,K) -> grad_vproj (V,3) (xy only; z receives nothing on this route).          */
 void occl_oracle_rasterize_backward(const float* vproj, const int32_t* faces, int V, int S, int K,
                                     int persp, const int32_t* pix_to_face,
                                     const float* grad_dists, double* grad_vproj) {
