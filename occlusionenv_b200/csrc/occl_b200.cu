@@ -47,7 +47,9 @@
 #define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
 #endif
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
-#define BIG_FACE_PX 128       // faces covering more tile pixels than this are rasterised by the whole CTA
+#ifndef BIG_FACE_PX
+#define BIG_FACE_PX 512       // faces covering more tile pixels than this are rasterised by the whole CTA
+#endif
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
 #define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
