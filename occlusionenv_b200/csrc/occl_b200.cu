@@ -274,6 +274,8 @@ struct RasterParams {
   int* n_live;   // [N]
   const uint32_t* tile_mask;  // [N][TILE_MASK_WORDS]
   const float2* shade;        // [N][F]
+  int* tile_idx;              // [N][n_tiles][tidx_cap] live-list indices of the faces that touch a tile
+  int tidx_cap;
   // outputs
   float* obs;
   float* occl;
@@ -844,7 +846,7 @@ raster_kernel(const RasterParams p) {
   const int tpx = tile_w * tile_h;
   const int S = p.S;
 
-  __shared__ int s_ovf_n, s_hit_n, s_chunk, s_big_n;
+  __shared__ int s_ovf_n, s_hit_n, s_chunk, s_big_n, s_tidx_n;
   __shared__ int s_wdef_n[OCCL_WARPS];
   __shared__ int s_ovf[OVF_CAP];
   __shared__ double s_red[OCCL_WARPS][4];
@@ -923,7 +925,7 @@ raster_kernel(const RasterParams p) {
     for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; }
+  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; s_tidx_n = 0; }
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
@@ -933,6 +935,7 @@ raster_kernel(const RasterParams p) {
   const uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
   const int n_live = p.n_live[env];
   const int tx1 = tx0 + tile_w - 1, ty1 = ty0 + tile_h - 1;
+  int* __restrict__ tidx = p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap;
 
   // ---- every warp on its own: scan a 32-face slice of the env's live list, stage the faces whose blur box
   // ---- overlaps the tile (ballot compaction) in the warp's buffer, scatter them, repeat.  No CTA barrier.
@@ -963,7 +966,13 @@ raster_kernel(const RasterParams p) {
           keep = cx0 <= cx1 && cy0 <= cy1;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        // remember which live faces touch this tile: the K-overflow passes rescan only those
+        int tbase = 0;
+        if (lane == 0 && bal) tbase = atomicAdd(&s_tidx_n, __popc(bal));
+        tbase = __shfl_sync(0xffffffffu, tbase, 0);
         if (keep) {
+          const int tpos = tbase + __popc(bal & ((1u << lane) - 1u));
+          if (tpos < p.tidx_cap) tidx[tpos] = k;
           const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
           const uint4* __restrict__ src = geo + (size_t)k * 4;
           uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
@@ -1120,6 +1129,9 @@ raster_kernel(const RasterParams p) {
   if (n_ovf > 0) {
     if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
     n_ovf = min(n_ovf, OVF_CAP);
+    // candidates: the tile's own face list if it fitted, else the env's whole live list
+    const bool use_tidx = s_tidx_n <= p.tidx_cap;
+    const int n_cand = use_tidx ? s_tidx_n : n_live;
     // selection buffers alias the (now idle) face list
     unsigned long long* hkey = (unsigned long long*)sm.list;            // [HIT_CAP]
     float* hq = (float*)(hkey + HIT_CAP);                               // [HIT_CAP]
@@ -1154,7 +1166,8 @@ raster_kernel(const RasterParams p) {
           s_opx[tid] = sm.ndc_x[lx]; s_opy[tid] = sm.ndc_y[ly];
         }
         __syncthreads();
-        for (int k = tid; k < n_live; k += OCCL_THREADS) {
+        for (int ci = tid; ci < n_cand; ci += OCCL_THREADS) {
+          const int k = use_tidx ? tidx[ci] : ci;
           const uint4 rg = __ldg(rng + k);
           const int rx0 = (int)(rg.x & 0xffffu), rx1 = (int)(rg.x >> 16), ry0 = (int)(rg.y & 0xffffu), ry1 = (int)(rg.y >> 16);
           if (rx1 < tx0 || rx0 > tx1 || ry1 < ty0 || ry0 > ty1) continue;
@@ -1261,7 +1274,8 @@ raster_kernel(const RasterParams p) {
       float pr = 1.0f, g0 = 0.f, g1 = 0.f;
       unsigned long long tau = 0ull;
       for (int scan = 0; scan < 2; ++scan) {
-        for (int k = tid; k < n_live; k += OCCL_THREADS) {
+        for (int ci = tid; ci < n_cand; ci += OCCL_THREADS) {
+          const int k = use_tidx ? tidx[ci] : ci;
           const uint4 rg = __ldg(rng + k);
           if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
           const uint4* __restrict__ src = geo + (size_t)k * 4;
@@ -1552,7 +1566,8 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, total;
+  int tidx_cap;
   int n_tiles;
 };
 
@@ -1635,6 +1650,8 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->n_live = off;   off = align_up(off + sizeof(int) * (size_t)n, 256);
   L->tile_mask = off; off = align_up(off + sizeof(uint32_t) * TILE_MASK_WORDS * (size_t)n, 256);
   L->shade = off;    off = align_up(off + sizeof(float2) * (size_t)n * c->n_faces, 256);
+  L->tidx_cap = c->n_faces < 8192 ? c->n_faces : 8192;
+  L->tile_idx = off; off = align_up(off + sizeof(int) * (size_t)n * L->n_tiles * L->tidx_cap, 256);
   L->total = off;
   return 0;
 }
@@ -1738,6 +1755,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.geo = (uint4*)(base + L.geo); p.rng = (uint4*)(base + L.rng); p.n_live = (int*)(base + L.n_live);
   p.tile_mask = (const uint32_t*)(base + L.tile_mask);
   p.shade = (const float2*)(base + L.shade);
+  p.tile_idx = (int*)(base + L.tile_idx); p.tidx_cap = L.tidx_cap;
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
   p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
