@@ -270,7 +270,7 @@ struct RasterParams {
   Partial* partials;
   // per-env compacted live faces (written by face_setup_kernel)
   uint4* geo;    // [N][F][4]  16 words per live face, see REC_* below
-  uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16)
+  uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16); object id in bits 30..31 of .w
   int* n_live;   // [N]
   const uint32_t* tile_mask;  // [N][TILE_MASK_WORDS]
   const float2* shade;        // [N][F]
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
                           __ldg(faces + 3 * f + 2), p.light, __ldg(cam + 12), __ldg(cam + 13), __ldg(cam + 14));
       }
       rng[slot] = make_uint4((uint32_t)sx0 | ((uint32_t)sx1 << 16), (uint32_t)sy0 | ((uint32_t)sy1 << 16),
-                             (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16));
+                             (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16) | (obj << 30));
     }
   }
   __syncthreads();
@@ -977,7 +977,7 @@ raster_kernel(const RasterParams p) {
           const uint4* __restrict__ src = geo + (size_t)k * 4;
           uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
           int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)(rg.z >> 16), tx1) - tx0;
-          int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)(rg.w >> 16), ty1) - ty0;
+          int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)((rg.w >> 16) & 0x3fffu), ty1) - ty0;
           if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
           q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
           q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
@@ -1255,10 +1255,12 @@ raster_kernel(const RasterParams p) {
         __syncthreads();
       }
     }
-    // One pixel at a time, for pixels with more hits than a batch sub-buffer holds: two scans of the live
-    // list.  Scan 1 collects only the sort keys (pz_clipped, face) -- KEY_CAP of them fit the selection
-    // buffer -- and the K-th smallest becomes the threshold; scan 2 re-evaluates the hits and multiplies
-    // those at or below the threshold.
+    // One pixel at a time, for pixels with more hits than a batch sub-buffer holds (dense meshes):
+    //  A. the faces of this tile whose blur box holds the pixel are compacted into a candidate list,
+    //  B. the candidates are evaluated densely (every thread has work) -> sort key (pz_clipped, face) and factor,
+    //  C. the K-th smallest key is found (rank counting for short lists, 8-bit radix select otherwise),
+    //  D. the factors at or below that key are multiplied (the differentiable kernel re-evaluates those hits
+    //     for their tangent terms).
     for (int oi = 0; oi < n_ovf; ++oi) {
       const int slot = s_ovf[oi];
       if (slot < 0) continue;
@@ -1267,76 +1269,144 @@ raster_kernel(const RasterParams p) {
       const int ly = pix / tile_w, lx = pix - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
-      constexpr int KEY_CAP = (HIT_CAP * 20) / 8;
+      constexpr int CAND_CAP = 2048;
+      static_assert((size_t)CAND_CAP * 12 <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "candidate buffers must fit the selection buffer");
+      unsigned long long* ckey = (unsigned long long*)sm.list;  // [CAND_CAP]
+      float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its factor
       __shared__ unsigned long long s_tau;
-      if (tid == 0) s_hit_n = 0;
+      __shared__ int s_hist[256];
+      __shared__ int s_sel[2];
+      if (tid == 0) { s_hit_n = 0; s_sel[0] = 0; }
       __syncthreads();
-      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
-      unsigned long long tau = 0ull;
-      for (int scan = 0; scan < 2; ++scan) {
-        for (int ci = tid; ci < n_cand; ci += OCCL_THREADS) {
-          const int k = use_tidx ? tidx[ci] : ci;
+      // A
+      for (int c0 = 0; c0 < n_cand; c0 += OCCL_THREADS) {
+        const int ci = c0 + tid;
+        bool ok = false;
+        int k = 0;
+        if (ci < n_cand) {
+          k = use_tidx ? tidx[ci] : ci;
           const uint4 rg = __ldg(rng + k);
-          if (xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) continue;
-          const uint4* __restrict__ src = geo + (size_t)k * 4;
-          const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-          const int f = (int)(q2.z & REC_FIDX_MASK);
-          if ((int)((q2.z >> REC_OBJ_SHIFT) & 3u) != obj) continue;
-          FaceGeo g;
-          g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
-          g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
-          g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
-          g.area = __uint_as_float(q2.y);
-          const PairResult r = eval_pair(g, px, py);
-          if (!r.inside && r.dist >= p.blur) continue;
-          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
-          const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
-          if (scan == 0) {
-            const int h = atomicAdd(&s_hit_n, 1);
-            if (h < KEY_CAP) hkey[h] = key;
-            continue;
-          }
-          if (key > tau) continue;
-          const float sd = r.inside ? -r.dist : r.dist;
-          const float prob = soft_prob(sd, p.sigma);
-          pr = pr * (1.0f - prob);
-          if (GRAD) {
-            const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-            const float4 ta = __ldg(vt + __ldg(faces + 3 * f + 0)), tb = __ldg(vt + __ldg(faces + 3 * f + 1)),
-                         tc = __ldg(vt + __ldg(faces + 3 * f + 2));
-            float ax, ay, bx, by;
-            float4 da, db;
-            if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
-            else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
-            else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
-            const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
-            const float sgn = r.inside ? -1.f : 1.f;
-            const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
-            const float wa = 1.f - r.t, wb = r.t;
-            const float kk = prob / p.sigma;
-            g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
-            g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
-          }
+          ok = !(xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) &&
+               (int)(rg.w >> 30) == obj;
         }
-        __syncthreads();
-        if (scan == 0) {
-          int nh = s_hit_n;
-          if (nh > KEY_CAP) {
-            if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
-            nh = KEY_CAP;
-          }
-          const int want = min(p.K, nh) - 1;  // rank of the last key kept
-          for (int a = tid; a < nh; a += OCCL_THREADS) {
-            const unsigned long long ka = hkey[a];
-            int rank = 0;
-            for (int b = 0; b < nh; ++b) rank += hkey[b] < ka;
-            if (rank == want) s_tau = ka;
-          }
-          __syncthreads();
-          tau = s_tau;
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        int base0 = 0;
+        if (lane == 0 && bal) base0 = atomicAdd(&s_hit_n, __popc(bal));
+        base0 = __shfl_sync(0xffffffffu, base0, 0);
+        if (ok) {
+          const int pos = base0 + __popc(bal & ((1u << lane) - 1u));
+          if (pos < CAND_CAP) ((int*)cq)[pos] = k;
         }
       }
-      // CTA product / sums of the selected hits
+      __syncthreads();
+      int nc = s_hit_n;
+      if (nc > CAND_CAP) {
+        if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
+        nc = CAND_CAP;
+      }
+      // B
+      int my_hits = 0;
+      for (int i = tid; i < nc; i += OCCL_THREADS) {
+        const int k = ((const int*)cq)[i];
+        const uint4* __restrict__ src = geo + (size_t)k * 4;
+        const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+        FaceGeo g;
+        g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+        g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+        g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+        g.area = __uint_as_float(q2.y);
+        const PairResult r = eval_pair(g, px, py);
+        unsigned long long key = ~0ull;
+        float q = 1.0f;
+        if (r.inside || r.dist < p.blur) {
+          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+          key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
+          q = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+          ++my_hits;
+        }
+        ckey[i] = key;
+        cq[i] = q;
+      }
+      if (my_hits) atomicAdd(&s_sel[0], my_hits);
+      __syncthreads();
+      const int nh = s_sel[0];
+      int want = min(p.K, nh) - 1;  // 0-based rank of the last key kept
+      // C
+      if (nc <= 512) {
+        for (int a = tid; a < nc; a += OCCL_THREADS) {
+          const unsigned long long ka = ckey[a];
+          int rank = 0;
+          for (int b = 0; b < nc; ++b) rank += ckey[b] < ka;
+          if (rank == want && ka != ~0ull) s_tau = ka;
+        }
+        __syncthreads();
+      } else {
+        unsigned long long prefix = 0ull, mask = 0ull;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+          s_hist[tid] = 0;  // OCCL_THREADS == 256 bins
+          __syncthreads();
+          for (int i = tid; i < nc; i += OCCL_THREADS) {
+            const unsigned long long key = ckey[i];
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
+          }
+          __syncthreads();
+          if (warp == 0) {
+            int cnt8[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { cnt8[b] = s_hist[lane * 8 + b]; sum += cnt8[b]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int excl = incl - sum;
+            if (want >= excl && want < incl) {
+              int r = want - excl, b = 0;
+              while (r >= cnt8[b]) { r -= cnt8[b]; ++b; }
+              s_sel[0] = lane * 8 + b;
+              s_sel[1] = r;
+            }
+          }
+          __syncthreads();
+          prefix |= (unsigned long long)s_sel[0] << shift;
+          mask |= 255ull << shift;
+          want = s_sel[1];
+          __syncthreads();
+        }
+        if (tid == 0) s_tau = prefix;
+        __syncthreads();
+      }
+      const unsigned long long tau = s_tau;
+      // D
+      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+      for (int i = tid; i < nc; i += OCCL_THREADS) {
+        const unsigned long long key = ckey[i];
+        if (key > tau) continue;
+        pr = pr * cq[i];
+        if (GRAD) {
+          const int f = (int)(key & 0xffffffffull);
+          const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+          FaceGeo g;
+          face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, &g);
+          const PairResult r = eval_pair(g, px, py);
+          const float prob = soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+          const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+          const float4 ta = __ldg(vt + i0), tb = __ldg(vt + i1), tc = __ldg(vt + i2);
+          float ax, ay, bx, by;
+          float4 da, db;
+          if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+          else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+          else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+          const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
+          const float sgn = r.inside ? -1.f : 1.f;
+          const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+          const float wa = 1.f - r.t, wb = r.t;
+          const float kk = prob / p.sigma;
+          g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+          g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
