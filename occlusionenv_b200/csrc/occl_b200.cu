@@ -51,7 +51,7 @@
 #define BIG_FACE_PX 512       // faces covering more tile pixels than this are rasterised by the whole CTA
 #endif
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
-#define HIT_CAP 1024          // top-K selection buffer (hits of ONE overflowing pixel)
+#define CAND_CAP 2048         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
 #define REC_WORDS 16
@@ -1133,9 +1133,6 @@ raster_kernel(const RasterParams p) {
     const bool use_tidx = s_tidx_n <= p.tidx_cap;
     const int n_cand = use_tidx ? s_tidx_n : n_live;
     // selection buffers alias the (now idle) face list
-    unsigned long long* hkey = (unsigned long long*)sm.list;            // [HIT_CAP]
-    float* hq = (float*)(hkey + HIT_CAP);                               // [HIT_CAP]
-    float* hg = hq + HIT_CAP;                                           // [2][HIT_CAP] (GRAD)
     // deterministic order of the overflow list (atomicAdd order is not): sort the small list
     if (tid == 0) {
       for (int a = 1; a < n_ovf; ++a) {
@@ -1146,116 +1143,7 @@ raster_kernel(const RasterParams p) {
       }
     }
     __syncthreads();
-    // Batched pass: OVB overflowing pixels share one scan of the live list; a warp then selects the K nearest
-    // hits of "its" pixel.  A pixel with more than HSUB hits is left to the one-pixel-at-a-time pass below.
-    {
-#ifndef OCCL_OVB
-#define OCCL_OVB 6
-#endif
-      constexpr int OVB = OCCL_OVB, HSUB = 160;
-      static_assert(OVB * HSUB <= HIT_CAP, "sub-buffers must fit the selection buffer");
-      __shared__ int s_ocnt[OVB], s_oxi[OVB], s_oyi[OVB], s_oobj[OVB];
-      __shared__ float s_opx[OVB], s_opy[OVB];
-      for (int o0 = 0; OVB > 1 && o0 < n_ovf; o0 += OVB) {
-        const int nb = min(OVB, n_ovf - o0);
-        if (tid < nb) {
-          const int slot = s_ovf[o0 + tid];
-          const int obj = slot / tpx, pix = slot - obj * tpx;
-          const int ly = pix / tile_w, lx = pix - ly * tile_w;
-          s_ocnt[tid] = 0; s_oobj[tid] = obj; s_oxi[tid] = tx0 + lx; s_oyi[tid] = ty0 + ly;
-          s_opx[tid] = sm.ndc_x[lx]; s_opy[tid] = sm.ndc_y[ly];
-        }
-        __syncthreads();
-        for (int ci = tid; ci < n_cand; ci += OCCL_THREADS) {
-          const int k = use_tidx ? tidx[ci] : ci;
-          const uint4 rg = __ldg(rng + k);
-          const int rx0 = (int)(rg.x & 0xffffu), rx1 = (int)(rg.x >> 16), ry0 = (int)(rg.y & 0xffffu), ry1 = (int)(rg.y >> 16);
-          if (rx1 < tx0 || rx0 > tx1 || ry1 < ty0 || ry0 > ty1) continue;
-          bool loaded = false;
-          FaceGeo g;
-          int f = 0, fobj = 0;
-          for (int j = 0; j < nb; ++j) {
-            const int xi = s_oxi[j], yi = s_oyi[j];
-            if (xi < rx0 || xi > rx1 || yi < ry0 || yi > ry1) continue;
-            if (!loaded) {
-              const uint4* __restrict__ src = geo + (size_t)k * 4;
-              const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-              f = (int)(q2.z & REC_FIDX_MASK);
-              fobj = (int)((q2.z >> REC_OBJ_SHIFT) & 3u);
-              g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
-              g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
-              g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
-              g.area = __uint_as_float(q2.y);
-              loaded = true;
-            }
-            if (fobj != s_oobj[j]) continue;
-            const float px = s_opx[j], py = s_opy[j];
-            const PairResult r = eval_pair(g, px, py);
-            if (!r.inside && r.dist >= p.blur) continue;
-            const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
-            const float sd = r.inside ? -r.dist : r.dist;
-            const float prob = soft_prob(sd, p.sigma);
-            const int hcount = atomicAdd(&s_ocnt[j], 1);
-            if (hcount < HSUB) {
-              const int h = j * HSUB + hcount;
-              hkey[h] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)f;
-              hq[h] = 1.0f - prob;
-              if (GRAD) {
-                const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-                const float4 ta = __ldg(vt + __ldg(faces + 3 * f + 0)), tb = __ldg(vt + __ldg(faces + 3 * f + 1)),
-                             tc = __ldg(vt + __ldg(faces + 3 * f + 2));
-                float ax, ay, bx, by;
-                float4 da, db;
-                if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
-                else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
-                else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
-                const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
-                const float sgn = r.inside ? -1.f : 1.f;
-                const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
-                const float wa = 1.f - r.t, wb = r.t;
-                const float kk = prob / p.sigma;
-                hg[h] = kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
-                hg[HIT_CAP + h] = kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
-              }
-            }
-          }
-        }
-        __syncthreads();
-        if (warp < nb) {
-          const int nh = s_ocnt[warp];
-          if (nh <= HSUB) {
-            const int hb0 = warp * HSUB;
-            float pr = 1.0f, g0 = 0.f, g1 = 0.f;
-            for (int a = lane; a < nh; a += 32) {
-              const unsigned long long ka = hkey[hb0 + a];
-              int rank = 0;
-              for (int b = 0; b < nh; ++b) rank += hkey[hb0 + b] < ka;
-              if (rank < p.K) {
-                pr = pr * hq[hb0 + a];
-                if (GRAD) { g0 += hg[hb0 + a]; g1 += hg[HIT_CAP + hb0 + a]; }
-              }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
-              if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
-            }
-            if (lane == 0) {
-              const int slot = s_ovf[o0 + warp];
-              const int obj = slot / tpx, pix = slot - obj * tpx;
-              const unsigned long long old = sm.soft[slot];
-              sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(pr);
-              if (GRAD) {
-                sm.gacc[(size_t)obj * tpx + pix] = pack2f(g0, g1);
-              }
-              s_ovf[o0 + warp] = -1;  // done
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    // One pixel at a time, for pixels with more hits than a batch sub-buffer holds (dense meshes):
+    // One pixel at a time:
     //  A. the faces of this tile whose blur box holds the pixel are compacted into a candidate list,
     //  B. the candidates are evaluated densely (every thread has work) -> sort key (pz_clipped, face) and factor,
     //  C. the K-th smallest key is found (rank counting for short lists, 8-bit radix select otherwise),
@@ -1269,7 +1157,6 @@ raster_kernel(const RasterParams p) {
       const int ly = pix / tile_w, lx = pix - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
-      constexpr int CAND_CAP = 2048;
       static_assert((size_t)CAND_CAP * 12 <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "candidate buffers must fit the selection buffer");
       unsigned long long* ckey = (unsigned long long*)sm.list;  // [CAND_CAP]
       float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its factor
@@ -1702,7 +1589,6 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
   if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
   // the top-K selection buffers alias the face list
-  if ((size_t)HIT_CAP * (8 + 4 + 8) > (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP)) return OCCL_E_INVALID;
   return OCCL_OK;
 }
 
