@@ -338,3 +338,59 @@ def test_dense_meshes_many_overflowing_pixels(oracle, cuda_lib, seed, az, el):
     eng2.render(Rt, Tt, Ct)
     assert torch.equal(eng.nhits, eng2.nhits) and torch.equal(eng.pix_to_face, eng2.pix_to_face)
     torch.testing.assert_close(eng.alphas, eng2.alphas, rtol=RTOL, atol=ATOL_A)
+
+
+@pytest.mark.parametrize("variant", ["far_camera", "k10", "no_cull", "norm_object_size", "tiny_image", "near_camera_flag"])
+def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
+    """Edge cases of the raster configuration: sub-pixel faces (all hits pile up on a few pixels), a small K
+    (the nearest-K rule everywhere), no back-face culling (negative-area faces take the reference-order path),
+    the normWithObjectSize reward branch (environment.py:324), a 16x16 image, and the z-clip flag."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    sc = default_scene("teapot")
+    S, K, cull, radius, norm = 64, 100, True, 4.0, False
+    if variant == "far_camera":
+        radius = 30.0
+    elif variant == "k10":
+        K = 10
+    elif variant == "no_cull":
+        cull = False
+    elif variant == "norm_object_size":
+        norm = True
+    elif variant == "tiny_image":
+        S = 16
+    elif variant == "near_camera_flag":
+        radius = 2.3  # closer than znear/2 to the shifted teapot
+    cfg = RasterConfig(image_size=S, faces_per_pixel=K, cull_backfaces=cull, norm_with_object_size=norm)
+    eng = OcclusionEngine(sc, 1, cfg, debug_outputs=True)
+    az, el = 1.45, 0.1
+    eng.reset(radius=radius, azimuth=az, elevation=el)
+    st = int(eng.status[0])
+    if variant == "near_camera_flag":
+        assert st & 1, "a vertex closer than znear/2 must raise the z-clip flag"
+        from occlusionenv_b200 import _lib as L
+        with pytest.raises(L.OcclError):
+            eng.check_status()
+        return
+    assert not (st & (1 | 4)), st
+    C, R, T = oracle.pose_lookat(radius, el, az)
+    vproj = oracle.project(sc.verts, R, T)
+    alphas, nhits = [], []
+    for i in range(sc.n_obj):
+        v0, v1 = sc.obj_vert_start[i], sc.obj_vert_start[i + 1]
+        f0, f1 = sc.obj_face_start[i], sc.obj_face_start[i + 1]
+        fr = oracle.rasterize(vproj[v0:v1], sc.faces[f0:f1] - v0, S, oracle.BLUR_RADIUS, K, cull_backfaces=cull)
+        alphas.append(oracle.silhouette(fr))
+        nhits.append(fr.nhits)
+    scene = oracle.rasterize(vproj, sc.faces, S, 0.0, 1, cull_backfaces=cull)
+    assert np.array_equal(eng.nhits[0].cpu().numpy(), np.stack(nhits))
+    assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), scene.pix_to_face[..., 0])
+    assert np.array_equal(eng.obs[0, 3].cpu().numpy(), scene.zbuf[..., 0])
+    np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), np.stack(alphas), rtol=RTOL, atol=ATOL_A)
+    occl = alphas[0] * alphas[1]
+    loss = float(np.sum(occl.astype(np.float64) ** 2))
+    np.testing.assert_allclose(float(eng.loss[0]), loss, rtol=RTOL, atol=1e-6)
+    objsq = float(np.sum((alphas[0] + alphas[1]).astype(np.float64) ** 2))
+    mass = (objsq if norm else loss) + 1.0
+    np.testing.assert_allclose(float(eng.object_mass[0]), mass, rtol=RTOL)
+    if variant in ("far_camera", "k10"):
+        assert (np.stack(nhits) > K).any()
