@@ -394,3 +394,71 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     np.testing.assert_allclose(float(eng.object_mass[0]), mass, rtol=RTOL)
     if variant in ("far_camera", "k10"):
         assert (np.stack(nhits) > K).any()
+
+
+def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
+    """Hand-made nasty geometry through occl_render with an identity camera: slivers with one edge shorter
+    than 1e-4 (degenerate-edge branch of the point-segment distance), needle triangles, exact duplicates
+    (depth ties -> lower face index), faces far outside the image, sub-pixel faces, pixel-centre-aligned
+    vertices, faces with |ndc| > 4 and clockwise faces (culled).  Every guard of the fast path has to hand these
+    to the reference-order routine or decide them identically."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    from occlusionenv_b200.meshes import pack_scene
+    rng = np.random.default_rng(7)
+    S = 64
+    s = float(oracle.PROJ_SCALE)
+    tris = []
+
+    def add(p0, p1, p2, z=(2.0, 2.0, 2.0)):
+        # p* are NDC xy; convert to view/world coordinates (identity camera): x_ndc = s x / z
+        tris.append([[p0[0] * z[0] / s, p0[1] * z[0] / s, z[0]], [p1[0] * z[1] / s, p1[1] * z[1] / s, z[1]],
+                     [p2[0] * z[2] / s, p2[1] * z[2] / s, z[2]]])
+
+    c = lambda i: -1.0 + (2 * i + 1) / S  # pixel centre
+    for _ in range(60):  # random small / medium faces, random depth per vertex
+        ctr = rng.uniform(-0.9, 0.9, 2)
+        r = 10 ** rng.uniform(-3, -0.5)
+        pts = ctr + rng.normal(size=(3, 2)) * r
+        add(*pts, z=tuple(rng.uniform(0.7, 5.0, 3)))
+    for _ in range(20):  # slivers: one edge ~1e-5 long
+        a = rng.uniform(-0.8, 0.8, 2)
+        b = a + rng.normal(size=2) * 1e-5
+        cc = a + rng.normal(size=2) * 0.3
+        add(a, b, cc)
+        add(a, cc, b)
+    for _ in range(10):  # needles
+        a = rng.uniform(-0.8, 0.8, 2)
+        d = rng.normal(size=2)
+        add(a, a + d * 0.5, a + d * 0.5 + np.array([-d[1], d[0]]) * 1e-4)
+        add(a, a + d * 0.5 + np.array([-d[1], d[0]]) * 1e-4, a + d * 0.5)
+    for i in (5, 20, 33):  # vertices exactly on pixel centres, duplicated faces (z ties)
+        p0, p1, p2 = (c(i), c(i)), (c(i + 6), c(i)), (c(i), c(i + 6))
+        add(p0, p1, p2)
+        add(p0, p1, p2)
+        add(p0, p2, p1)
+    add((-6.0, -6.0), (6.5, -6.0), (0.0, 7.0), z=(3.0, 3.0, 3.0))   # huge, |ndc| > 4 (not fast)
+    add((-6.0, -6.0), (0.0, 7.0), (6.5, -6.0), z=(3.0, 3.0, 3.0))
+    add((1.5, 1.5), (1.7, 1.5), (1.5, 1.8))                           # off screen
+    add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 3e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4))  # sub-pixel
+    add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4), (c(10) + 3e-4, c(10) + 1e-4))
+    tris = np.asarray(tris, np.float32)
+    verts = tris.reshape(-1, 3)
+    faces = np.arange(len(verts), dtype=np.int32).reshape(-1, 3)
+    half = len(faces) // 2
+    sc = pack_scene([(verts[:half * 3], faces[:half]), (verts[half * 3:], faces[half:] - half * 3)])
+    R = np.eye(3, dtype=np.float32)
+    T = np.zeros(3, np.float32)
+    C = np.zeros(3, np.float32)
+    ref = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
+    for exact in (False, True):
+        eng = OcclusionEngine(sc, 1, RasterConfig(image_size=S, debug_exact=exact), debug_outputs=True)
+        Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
+        eng.render(Rt, Tt, Ct)
+        assert not (int(eng.status[0]) & (1 | 4))
+        assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits), exact
+        assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), ref.pix_to_face), exact
+        assert np.array_equal(eng.obs[0, 3].cpu().numpy(), ref.obs[3]), exact
+        assert np.array_equal(eng.n_covered[0].cpu().numpy(), ref.n_covered)
+        assert np.array_equal(eng.n_visible[0].cpu().numpy(), ref.n_visible)
+        np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
+        np.testing.assert_allclose(eng.obs[0, :3].cpu().numpy(), ref.obs[:3], rtol=RTOL, atol=1e-6)
