@@ -45,7 +45,10 @@ def make_poses(n, seed, offset=0):
     az = (math.pi / 2 - 0.6) + 1.2 * torch.rand(n, generator=g)
     el = -0.3 + 0.6 * torch.rand(n, generator=g)
     ga = torch.Generator().manual_seed(seed + 1 + offset)
-    actions = torch.randn(8, n, 2, generator=ga)
+    a = torch.randn(4, n, 2, generator=ga)
+    # a, -a, b, -b, ...: unit steps that cancel in pairs, so the pose distribution (and with it the work per
+    # step) stays the one of the reset however many steps are timed
+    actions = torch.stack([a[0], -a[0], a[1], -a[1], a[2], -a[2], a[3], -a[3]])
     return az, el, actions
 
 
