@@ -621,10 +621,11 @@ __device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
 }
 
 // soft accumulator word: low 32 bits = running product of (1 - prob) as float bits,
-// high 32 bits = hit count (bits 0..14) | count of "weak" hits with 1 - prob > 1/4 (bits 15..29) |
-//                top-K resolved flag (bit 30) | hard-covered flag (bit 31)
-#define SOFT_CNT_MASK 0x7fffu
-#define SOFT_WEAK_SHIFT 15
+// high 32 bits = hit count (bits 0..19) | count of "weak" hits with 1 - prob > 1/4, saturating at 1023
+//                (bits 20..29) | top-K resolved flag (bit 30) | hard-covered flag (bit 31)
+#define SOFT_CNT_MASK 0xfffffu
+#define SOFT_WEAK_MASK 0x3ffu
+#define SOFT_WEAK_SHIFT 20
 #define SOFT_RESOLVED 0x40000000u
 #define SOFT_STRONG_NEEDED 13  // 0.25^13 < 2^-25: that many strong factors make 1 - product == 1.0f exactly
 __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float q, bool covered) {
@@ -632,7 +633,8 @@ __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float 
   do {
     assumed = old;
     const float pr = __uint_as_float((unsigned)(assumed & 0xffffffffull)) * q;
-    unsigned hi = (unsigned)(assumed >> 32) + (q > 0.25f ? 1u + (1u << SOFT_WEAK_SHIFT) : 1u);
+    unsigned hi = (unsigned)(assumed >> 32);
+    hi += (q > 0.25f && ((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK) != SOFT_WEAK_MASK) ? 1u + (1u << SOFT_WEAK_SHIFT) : 1u;
     if (covered) hi |= 0x80000000u;
     const unsigned long long nw = ((unsigned long long)hi << 32) | (unsigned long long)__float_as_uint(pr);
     old = atomicCAS(slot, assumed, nw);
@@ -1112,7 +1114,7 @@ raster_kernel(const RasterParams p) {
       // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
       // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
       // reference's alpha is exactly 1.0f: no selection needed.
-      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_CNT_MASK);
+      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
       if (p.K - weak >= SOFT_STRONG_NEEDED) {
         sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
         if (GRAD) sm.gacc[i] = 0ull;
@@ -1576,6 +1578,7 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->n_obj < 1 || c->n_obj > OCCL_MAX_OBJ) return OCCL_E_INVALID;
   if (c->n_verts < 1 || c->n_faces < 1) return OCCL_E_INVALID;
   if (c->faces_per_pixel < 1 || c->faces_per_pixel > 128) return OCCL_E_INVALID;
+  if (c->n_faces >= (1 << 28)) return OCCL_E_INVALID;  // packed face index field
   if (c->obj_face_start[0] != 0 || c->obj_face_start[c->n_obj] != c->n_faces) return OCCL_E_INVALID;
   for (int i = 0; i < c->n_obj; ++i)
     if (c->obj_face_start[i + 1] < c->obj_face_start[i]) return OCCL_E_INVALID;
