@@ -53,7 +53,10 @@
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
 #define CAND_CAP 2048         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
-#define OVF_CAP 128           // overflowing (pixel, object) pairs handled per tile
+#define OVF_CAP 128           // overflowing (pixel, object) pairs handled per round of the one-pixel fallback
+#define HITBUF_CAP 2176       // hits (12 B each) of one selection round: aliases the face list + depth queue
+#define WQ_CAP 64             // (slot, face) pairs queued per warp for the dense evaluation of a round
+#define RSLOT_CAP 128         // (pixel, object) slots per selection round (table aliases the big-face records)
 #define REC_WORDS 16
 
 static thread_local char g_last_err[256] = "";
@@ -235,7 +238,6 @@ __global__ void project_kernel(long long total, int V, const float* __restrict__
   const float xn = (s * xv) / zv;
   const float yn = (s * yv) / zv;
   vproj[idx] = make_float4(xn, yn, zv, 0.f);
-  if (zv < z_clip && status) atomicOr(status + e, OCCL_ST_ZCLIP);
   if (GRAD) {
     float t[4];
 #pragma unroll
@@ -430,8 +432,12 @@ __device__ __forceinline__ void ndc_range_to_pixels(const float* __restrict__ ta
   *i1 = b;
 }
 
-// Pixel-independent part of CheckPixelInsideFace: the culls and `area`.
-__device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const float4 c, int cull, FaceGeo* gp) {
+// Pixel-independent part of CheckPixelInsideFace: the culls and `area`, preceded by the part of
+// pytorch3d's clip_faces (renderer/mesh/clip.py) that needs no new geometry: a face whose three vertices are
+// all nearer than z_clip is removed; a face that straddles z_clip would be cut into one or two new triangles
+// there -- not implemented: *straddles is reported and the caller raises OCCL_ST_ZCLIP.
+__device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const float4 c, int cull, float z_clip,
+                                         FaceGeo* gp, bool* straddles) {
   FaceGeo& g = *gp;
   g.x0 = a.x; g.y0 = a.y; g.z0 = a.z;
   g.x1 = b.x; g.y1 = b.y; g.z1 = b.z;
@@ -441,6 +447,8 @@ __device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const f
   const float zmax = fmaxf(fmaxf(g.z0, g.z1), g.z2);
   const float zmin = fminf(fminf(g.z0, g.z1), g.z2);
   bool skip = zmax < 0.f;
+  skip |= zmax < z_clip;
+  *straddles = !(zmax < z_clip) && zmin < z_clip;
   skip |= (cull && face_area < 0.f);
   skip |= ((double)face_area <= 1e-8 && (double)face_area >= -1e-8);
   skip |= ((double)zmin < 1e-8);
@@ -497,6 +505,8 @@ __device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, in
 // ----------------------------------------------------------------------------------------------
 struct SetupParams {
   int S, V, F, cull, n_obj;
+  float z_clip;
+  uint32_t* status;
   int obj_face_start[OCCL_MAX_OBJ + 1];
   int tile_w, tile_h, tiles_x, n_tiles;
   float inv_tile_w, inv_tile_h;
@@ -542,7 +552,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
     int sx0 = 0, sx1 = -1, sy0 = 0, sy1 = -1, hx0 = 0, hx1 = -1, hy0 = 0, hy1 = -1;
     if (f < p.F) {
       const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
-      live = face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, &g);
+      bool straddles = false;
+      live = face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, p.z_clip, &g, &straddles);
+      if (straddles) atomicOr(p.status + env, OCCL_ST_ZCLIP);
       if (live) {
         const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
         const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
@@ -621,11 +633,13 @@ __device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
 }
 
 // soft accumulator word: low 32 bits = running product of (1 - prob) as float bits,
-// high 32 bits = hit count (bits 0..19) | count of "weak" hits with 1 - prob > 1/4, saturating at 1023
-//                (bits 20..29) | top-K resolved flag (bit 30) | hard-covered flag (bit 31)
+// high 32 bits = hit count (bits 0..19) | count of "weak" hits with 1 - prob > 1/4, saturating at 511
+//                (bits 20..28) | member of the current selection round (bit 29; the low word is then the
+//                write cursor of the pixel's hit list) | top-K resolved flag (bit 30) | hard-covered flag (bit 31)
 #define SOFT_CNT_MASK 0xfffffu
-#define SOFT_WEAK_MASK 0x3ffu
+#define SOFT_WEAK_MASK 0x1ffu
 #define SOFT_WEAK_SHIFT 20
+#define SOFT_ROUND 0x20000000u
 #define SOFT_RESOLVED 0x40000000u
 #define SOFT_STRONG_NEEDED 13  // 0.25^13 < 2^-25: that many strong factors make 1 - product == 1.0f exactly
 __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float q, bool covered) {
@@ -666,6 +680,23 @@ struct TileSmem {
   uint32_t* big;             // [BIG_CAP][REC_WORDS] faces set aside for CTA-wide rasterisation
   int* defer_n;
 };
+
+// Shared-memory layout of a tile: fixed-size regions first so that, with a compile-time tile, every base
+// address is a constant.
+__device__ __forceinline__ TileSmem tile_smem_layout(unsigned char* q, const int tile_w, const int tile_h, const int n_obj) {
+  TileSmem sm;
+  const int tpx = tile_w * tile_h;
+  sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
+  sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
+  sm.big = (uint32_t*)q;             q += sizeof(uint32_t) * BIG_CAP * REC_WORDS;
+  sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
+  sm.ndc_x = (float*)q;              q += sizeof(float) * ((tile_w + 1) & ~1);
+  sm.ndc_y = (float*)q;              q += sizeof(float) * ((tile_h + 1) & ~1);
+  sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * n_obj;
+  sm.gacc = (unsigned long long*)q;
+  sm.defer_n = nullptr;
+  return sm;
+}
 
 __device__ __forceinline__ void load_geo(const uint32_t* __restrict__ rec, FaceGeo* g) {
   g->x0 = __uint_as_float(rec[0]); g->y0 = __uint_as_float(rec[1]); g->z0 = __uint_as_float(rec[2]);
@@ -820,6 +851,33 @@ __device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const 
   }
 }
 
+// Tangent terms of one soft hit, re-evaluated from the face index (K-overflow selection of the differentiable
+// kernel): adds p_k/sigma * d(signed dist)/d(el, az)  (SURVEY A.7).
+__device__ __noinline__ void hit_tangent(const RasterParams& p, int env, int f, float px, float py, float* g0, float* g1) {
+  const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
+  const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
+  const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+  FaceGeo g;
+  bool straddles_unused;
+  face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, 0.f, &g, &straddles_unused);
+  const PairResult r = eval_pair(g, px, py);
+  const float prob = soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+  const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+  const float4 ta = __ldg(vt + i0), tb = __ldg(vt + i1), tc = __ldg(vt + i2);
+  float ax, ay, bx, by;
+  float4 da, db;
+  if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
+  else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
+  else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
+  const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
+  const float sgn = r.inside ? -1.f : 1.f;
+  const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+  const float wa = 1.f - r.t, wb = r.t;
+  const float kk = prob / p.sigma;
+  *g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+  *g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -829,6 +887,426 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
+}
+
+// K-overflow resolution of one tile.  Inlined into the kernel (a non-inlined call measured 5-10 % slower on the
+// main phase: ptxas' register allocation of the barrier-free loop is sensitive to what surrounds it); everything
+// is recomputed here so that nothing extra stays live across the caller's main phase.
+template <bool GRAD, int TW, int TH>
+__device__ __forceinline__ void koverflow_resolve(const RasterParams p, const int env, const int tile, const int n_tidx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
+  const int tpx = tile_w * tile_h;
+  const int tx0 = (tile % p.tiles_x) * tile_w, ty0 = (tile / p.tiles_x) * tile_h;
+  const TileSmem sm = tile_smem_layout(smem_raw, tile_w, tile_h, p.n_obj);
+  const int n_live = p.n_live[env];
+  const int* __restrict__ tidx = p.tile_idx + ((size_t)env * (p.tiles_x * p.tiles_y) + tile) * p.tidx_cap;
+  __shared__ double s_red[OCCL_WARPS][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
+  const uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
+  __shared__ int s_ovf_n, s_hit_n;
+  __shared__ int s_ovf[OVF_CAP];
+  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; }
+  // ---- pixels with more than K hits, hit-list rounds -------------------------------------------
+  // The reference keeps the K nearest hits by (pz_clipped, face index).  A round takes the next unresolved
+  // (pixel, object) slots -- in slot order, as many as their exactly known hit counts fit HITBUF_CAP -- and
+  //  1. marks them (bit 29; the product word becomes the write cursor of the slot's segment),
+  //  2. re-evaluates the faces of the tile that touch the round's pixel box with the reference-order routine
+  //     (8 lanes per face) and appends (key, factor) of every hit on a marked slot to its segment,
+  //  3. one warp per slot finds the K-th smallest key by bisection over the key bits (early exit once the
+  //     K smallest are separated) and multiplies the factors below it.
+  // Slots with more hits than a whole round holds are left to the one-pixel path below.
+  {
+    unsigned long long* hkey = (unsigned long long*)sm.list;  // [HITBUF_CAP]
+    float* hq = (float*)(hkey + HITBUF_CAP);                    // [HITBUF_CAP]
+    static_assert((size_t)HITBUF_CAP * 12 + 4 * OCCL_WARPS * WQ_CAP <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "hit buffer + pair queues must fit the face list");
+    __shared__ int s_rn, s_rb[4], s_wsum[OCCL_WARPS];
+    __shared__ unsigned s_robj;
+    int* s_rslot = (int*)sm.big;                                        // [RSLOT_CAP]  (big faces are done)
+    unsigned short* s_roff = (unsigned short*)(s_rslot + RSLOT_CAP);    // [RSLOT_CAP]
+    static_assert(RSLOT_CAP * 6 <= 4 * BIG_CAP * REC_WORDS, "round table must fit the big-face records");
+    const int n_slots = tpx * p.n_obj;
+    const int per = (n_slots + OCCL_THREADS - 1) / OCCL_THREADS;
+    const int s_begin = min(tid * per, n_slots), s_end = min(s_begin + per, n_slots);
+    const bool use_tidx = n_tidx <= p.tidx_cap;
+    const int n_cand = use_tidx ? n_tidx : n_live;
+    for (;;) {
+      if (tid == 0) { s_rn = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
+      int loc = 0;
+      for (int i = s_begin; i < s_end; ++i) {
+        const unsigned hi = (unsigned)(sm.soft[i] >> 32);
+        const int cnt = (int)(hi & SOFT_CNT_MASK);
+        if (cnt > p.K && !(hi & SOFT_RESOLVED)) {
+          // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
+          // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
+          // reference's alpha is exactly 1.0f: no selection needed.
+          const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
+          if (p.K - weak >= SOFT_STRONG_NEEDED) {
+            sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
+            if (GRAD) sm.gacc[i] = 0ull;
+            atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+          } else if (cnt <= HITBUF_CAP) {
+            loc += cnt;
+          }
+        }
+      }
+      int incl = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int off = incl - loc;
+      for (int w = 0; w < warp; ++w) off += s_wsum[w];
+      for (int i = s_begin; i < s_end && off < HITBUF_CAP; ++i) {
+        const unsigned hi = (unsigned)(sm.soft[i] >> 32);
+        const int cnt = (int)(hi & SOFT_CNT_MASK);
+        if (cnt > p.K && !(hi & SOFT_RESOLVED) && cnt <= HITBUF_CAP) {
+          if (off + cnt <= HITBUF_CAP) {
+            const int r = atomicAdd(&s_rn, 1);
+            if (r < RSLOT_CAP) {
+              s_rslot[r] = i;
+              s_roff[r] = (unsigned short)off;
+              const unsigned h2 = (hi & ~(SOFT_WEAK_MASK << SOFT_WEAK_SHIFT)) | SOFT_ROUND;
+              sm.soft[i] = ((unsigned long long)h2 << 32) | (unsigned long long)(unsigned)off;
+              const int obj = i / tpx, pix = i - obj * tpx;
+              const int ly = pix / tile_w, lx = pix - ly * tile_w;
+              atomicMin(&s_rb[0], lx); atomicMin(&s_rb[1], ly); atomicMax(&s_rb[2], lx); atomicMax(&s_rb[3], ly);
+              atomicOr(&s_robj, 1u << obj);
+            }
+          }
+          off += cnt;
+        }
+      }
+      __syncthreads();
+      const int rn = p.F <= (1 << 25) ? min(s_rn, RSLOT_CAP) : 0;  // queue entries hold 25 bits of face index
+      if (rn == 0) break;
+      if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+      // 2. (slot, face) pairs whose blur box holds the slot's pixel: lanes <-> faces of the tile, the round's
+      //    slots in turn; the pairs are compacted into a per-warp queue and evaluated 32 at a time with the
+      //    reference-order routine (every lane busy), hits are appended to the slot's segment.
+      {
+        const int bx0 = tx0 + s_rb[0], by0 = ty0 + s_rb[1], bx1 = tx0 + s_rb[2], by1 = ty0 + s_rb[3];
+        const unsigned robj = s_robj;
+        uint32_t* wq = (uint32_t*)(hq + HITBUF_CAP) + warp * WQ_CAP;
+        int qn = 0;  // warp-uniform
+        auto drain = [&](const bool flush) {
+          while (qn >= 32 || (flush && qn > 0)) {
+            const int take = min(qn, 32);
+            qn -= take;
+            if (lane < take) {
+              const uint32_t ent = wq[qn + lane];
+              const int slot = s_rslot[ent >> 25];
+              const int obj = slot / tpx, pix = slot - obj * tpx;
+              const int ly = pix / tile_w, lx = pix - ly * tile_w;
+              const uint4* __restrict__ srcg = geo + (size_t)(ent & 0x1ffffffu) * 4;
+              const uint4 q0 = __ldg(srcg + 0), q1 = __ldg(srcg + 1), q2 = __ldg(srcg + 2);
+              FaceGeo g;
+              g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+              g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+              g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+              g.area = __uint_as_float(q2.y);
+              const PairResult r = eval_pair(g, sm.ndc_x[lx], sm.ndc_y[ly]);
+              if (r.inside || r.dist < p.blur) {
+                const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+                const unsigned pos = atomicAdd((unsigned*)(sm.soft + slot), 1u);  // low word = cursor
+                if (pos < HITBUF_CAP) {
+                  hkey[pos] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
+                  hq[pos] = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+                }
+              }
+            }
+            __syncwarp();
+          }
+        };
+        for (int c0 = warp * 32; c0 < n_cand; c0 += OCCL_THREADS) {
+          const int ci = c0 + lane;
+          bool ok = false;
+          int k = 0;
+          uint4 rg = make_uint4(0, 0, 0, 0);
+          if (ci < n_cand) {
+            k = use_tidx ? tidx[ci] : ci;
+            rg = __ldg(rng + k);
+            ok = !(bx1 < (int)(rg.x & 0xffffu) || bx0 > (int)(rg.x >> 16) || by1 < (int)(rg.y & 0xffffu) || by0 > (int)(rg.y >> 16)) &&
+                 ((robj >> (rg.w >> 30)) & 1u);
+          }
+          if (!__any_sync(0xffffffffu, ok)) continue;
+          const int fx0 = (int)(rg.x & 0xffffu) - tx0, fx1 = (int)(rg.x >> 16) - tx0;
+          const int fy0 = (int)(rg.y & 0xffffu) - ty0, fy1 = (int)(rg.y >> 16) - ty0;
+          const int fobj = (int)(rg.w >> 30);
+          for (int r = 0; r < rn; ++r) {
+            const int slot = s_rslot[r];
+            const int obj = slot / tpx, pix = slot - obj * tpx;
+            const int ly = pix / tile_w, lx = pix - ly * tile_w;
+            const bool in = ok && obj == fobj && lx >= fx0 && lx <= fx1 && ly >= fy0 && ly <= fy1;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            if (!bal) continue;
+            if (in) wq[qn + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)r << 25) | (uint32_t)k;
+            qn += __popc(bal);
+            __syncwarp();
+            drain(false);
+          }
+        }
+        drain(true);
+      }
+      __syncthreads();
+      // 3. one warp per slot: K-th smallest key, product of the factors up to it
+      for (int r = warp; r < rn; r += OCCL_WARPS) {
+        const int slot = s_rslot[r];
+        const int off = (int)s_roff[r];
+        const unsigned long long w = sm.soft[slot];
+        const unsigned hi = (unsigned)(w >> 32);
+        const int cnt = (int)(hi & SOFT_CNT_MASK);
+        const int got = (int)(unsigned)(w & 0xffffffffull) - off;
+        if (got != cnt && lane == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);  // re-evaluation disagrees with the main phase
+        const int nn = max(min(got, min(cnt, HITBUF_CAP - off)), 0);
+        const unsigned long long* __restrict__ keys = hkey + off;
+        unsigned long long vand = ~0ull, vor = 0ull;
+        for (int i = lane; i < nn; i += 32) { const unsigned long long kx = keys[i]; vand &= kx; vor |= kx; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+          vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+        }
+        const unsigned long long diff = vand ^ vor;
+        const int want = min(p.K, nn) - 1;  // 0-based rank of the last key kept
+        unsigned long long bound = ~0ull;   // keys < bound are kept
+        if (nn > p.K && diff) {
+          const int top = 63 - __clzll((long long)diff);
+          unsigned long long prefix = top == 63 ? 0ull : (vor & ~((2ull << top) - 1ull));
+          bool found = false;
+          for (int bit = top; bit >= 0; --bit) {
+            const unsigned long long m = 1ull << bit;
+            if (!(diff & m)) { prefix |= vand & m; continue; }
+            const unsigned long long cand = prefix | m;
+            int c = 0;
+            for (int i = lane; i < nn; i += 32) c += keys[i] < cand ? 1 : 0;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c <= want) prefix = cand;
+            else if (c == want + 1) { bound = cand; found = true; break; }
+          }
+          if (!found) bound = prefix + 1ull;
+        }
+        float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+        const int obj = slot / tpx, pix = slot - obj * tpx;
+        const int ly = pix / tile_w, lx = pix - ly * tile_w;
+        for (int i = lane; i < nn; i += 32) {
+          const unsigned long long key = keys[i];
+          if (!(key < bound)) continue;
+          pr = pr * hq[off + i];
+          if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+          if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+        }
+        if (lane == 0) {
+          sm.soft[slot] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32) | (unsigned long long)__float_as_uint(pr);
+          if (GRAD) sm.gacc[slot] = pack2f(g0, g1);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- pixels with more hits than a round holds: one pixel at a time, whole CTA -----------------
+  // Rounds of at most OVF_CAP pixels; a resolved pixel carries bit 30 of its count word.
+  for (bool more = true; more;) {
+  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
+    const unsigned hi = (unsigned)(sm.soft[i] >> 32);
+    if ((int)(hi & SOFT_CNT_MASK) > p.K && !(hi & SOFT_RESOLVED)) {
+      // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
+      // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
+      // reference's alpha is exactly 1.0f: no selection needed.
+      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
+      if (p.K - weak >= SOFT_STRONG_NEEDED) {
+        sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
+        if (GRAD) sm.gacc[i] = 0ull;
+        atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+      } else {
+        const int s = atomicAdd(&s_ovf_n, 1);
+        if (s < OVF_CAP) s_ovf[s] = i;
+      }
+    }
+  }
+  __syncthreads();
+  int n_ovf = s_ovf_n;
+  more = n_ovf > OVF_CAP;
+  if (n_ovf > 0) {
+    if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+    n_ovf = min(n_ovf, OVF_CAP);
+    // candidates: the tile's own face list if it fitted, else the env's whole live list
+    const bool use_tidx = n_tidx <= p.tidx_cap;
+    const int n_cand = use_tidx ? n_tidx : n_live;
+    // selection buffers alias the (now idle) face list
+    // deterministic order of the overflow list (atomicAdd order is not): sort the small list
+    if (tid == 0) {
+      for (int a = 1; a < n_ovf; ++a) {
+        const int v = s_ovf[a];
+        int b = a - 1;
+        while (b >= 0 && s_ovf[b] > v) { s_ovf[b + 1] = s_ovf[b]; --b; }
+        s_ovf[b + 1] = v;
+      }
+    }
+    __syncthreads();
+    // One pixel at a time:
+    //  A. the faces of this tile whose blur box holds the pixel are compacted into a candidate list,
+    //  B. the candidates are evaluated densely (every thread has work) -> sort key (pz_clipped, face) and factor,
+    //  C. the K-th smallest key is found (rank counting for short lists, 8-bit radix select otherwise),
+    //  D. the factors at or below that key are multiplied (the differentiable kernel re-evaluates those hits
+    //     for their tangent terms).
+    for (int oi = 0; oi < n_ovf; ++oi) {
+      const int slot = s_ovf[oi];
+      if (slot < 0) continue;
+      const int obj = slot / tpx;
+      const int pix = slot - obj * tpx;
+      const int ly = pix / tile_w, lx = pix - ly * tile_w;
+      const int xi = tx0 + lx, yi = ty0 + ly;
+      const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
+      static_assert((size_t)CAND_CAP * 12 <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "candidate buffers must fit the selection buffer");
+      unsigned long long* ckey = (unsigned long long*)sm.list;  // [CAND_CAP]
+      float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its factor
+      __shared__ unsigned long long s_tau;
+      __shared__ int s_hist[256];
+      __shared__ int s_sel[2];
+      if (tid == 0) { s_hit_n = 0; s_sel[0] = 0; }
+      __syncthreads();
+      // A
+      for (int c0 = 0; c0 < n_cand; c0 += OCCL_THREADS) {
+        const int ci = c0 + tid;
+        bool ok = false;
+        int k = 0;
+        if (ci < n_cand) {
+          k = use_tidx ? tidx[ci] : ci;
+          const uint4 rg = __ldg(rng + k);
+          ok = !(xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) &&
+               (int)(rg.w >> 30) == obj;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        int base0 = 0;
+        if (lane == 0 && bal) base0 = atomicAdd(&s_hit_n, __popc(bal));
+        base0 = __shfl_sync(0xffffffffu, base0, 0);
+        if (ok) {
+          const int pos = base0 + __popc(bal & ((1u << lane) - 1u));
+          if (pos < CAND_CAP) ((int*)cq)[pos] = k;
+        }
+      }
+      __syncthreads();
+      int nc = s_hit_n;
+      if (nc > CAND_CAP) {
+        if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
+        nc = CAND_CAP;
+      }
+      // B
+      int my_hits = 0;
+      for (int i = tid; i < nc; i += OCCL_THREADS) {
+        const int k = ((const int*)cq)[i];
+        const uint4* __restrict__ src = geo + (size_t)k * 4;
+        const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+        FaceGeo g;
+        g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
+        g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
+        g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
+        g.area = __uint_as_float(q2.y);
+        const PairResult r = eval_pair(g, px, py);
+        unsigned long long key = ~0ull;
+        float q = 1.0f;
+        if (r.inside || r.dist < p.blur) {
+          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+          key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
+          q = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+          ++my_hits;
+        }
+        ckey[i] = key;
+        cq[i] = q;
+      }
+      if (my_hits) atomicAdd(&s_sel[0], my_hits);
+      __syncthreads();
+      const int nh = s_sel[0];
+      int want = min(p.K, nh) - 1;  // 0-based rank of the last key kept
+      // C
+      if (nc <= 512) {
+        for (int a = tid; a < nc; a += OCCL_THREADS) {
+          const unsigned long long ka = ckey[a];
+          int rank = 0;
+          for (int b = 0; b < nc; ++b) rank += ckey[b] < ka;
+          if (rank == want && ka != ~0ull) s_tau = ka;
+        }
+        __syncthreads();
+      } else {
+        unsigned long long prefix = 0ull, mask = 0ull;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+          s_hist[tid] = 0;  // OCCL_THREADS == 256 bins
+          __syncthreads();
+          for (int i = tid; i < nc; i += OCCL_THREADS) {
+            const unsigned long long key = ckey[i];
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
+          }
+          __syncthreads();
+          if (warp == 0) {
+            int cnt8[8], sum = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { cnt8[b] = s_hist[lane * 8 + b]; sum += cnt8[b]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int excl = incl - sum;
+            if (want >= excl && want < incl) {
+              int r = want - excl, b = 0;
+              while (r >= cnt8[b]) { r -= cnt8[b]; ++b; }
+              s_sel[0] = lane * 8 + b;
+              s_sel[1] = r;
+            }
+          }
+          __syncthreads();
+          prefix |= (unsigned long long)s_sel[0] << shift;
+          mask |= 255ull << shift;
+          want = s_sel[1];
+          __syncthreads();
+        }
+        if (tid == 0) s_tau = prefix;
+        __syncthreads();
+      }
+      const unsigned long long tau = s_tau;
+      // D
+      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+      for (int i = tid; i < nc; i += OCCL_THREADS) {
+        const unsigned long long key = ckey[i];
+        if (key > tau) continue;
+        pr = pr * cq[i];
+        if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), px, py, &g0, &g1);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+        if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+      }
+      if (lane == 0) { s_red[warp][0] = (double)pr; s_red[warp][1] = (double)g0; s_red[warp][2] = (double)g1; }
+      __syncthreads();
+      if (tid == 0) {
+        float P = 1.0f, G0 = 0.f, G1 = 0.f;
+        for (int w = 0; w < OCCL_WARPS; ++w) { P = P * (float)s_red[w][0]; G0 += (float)s_red[w][1]; G1 += (float)s_red[w][2]; }
+        const unsigned long long old = sm.soft[slot];
+        sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(P);
+        if (GRAD) sm.gacc[(size_t)obj * tpx + pix] = pack2f(G0, G1);
+      }
+      __syncthreads();
+    }
+  }
+  if (more) {
+    __syncthreads();
+    if (tid == 0) s_ovf_n = 0;
+    __syncthreads();
+  }
+  }
+
 }
 
 // TW, TH: compile-time tile shape (0 = take it from the parameters); the fixed 32x32 instantiation turns
@@ -848,26 +1326,13 @@ raster_kernel(const RasterParams p) {
   const int tpx = tile_w * tile_h;
   const int S = p.S;
 
-  __shared__ int s_ovf_n, s_hit_n, s_chunk, s_big_n, s_tidx_n;
+  __shared__ int s_chunk, s_big_n, s_tidx_n;
   __shared__ int s_wdef_n[OCCL_WARPS];
-  __shared__ int s_ovf[OVF_CAP];
   __shared__ double s_red[OCCL_WARPS][4];
   __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
 
-  TileSmem sm;
-  {
-    // fixed-size regions first so that, with a compile-time tile, every base address is a constant
-    unsigned char* q = smem_raw;
-    sm.list = (uint32_t*)q;            q += sizeof(uint32_t) * OCCL_WARPS * WBUF_RECS * REC_WORDS;
-    sm.defer = (uint32_t*)q;           q += sizeof(uint32_t) * OCCL_WARPS * WDEFER_CAP;
-    sm.big = (uint32_t*)q;             q += sizeof(uint32_t) * BIG_CAP * REC_WORDS;
-    sm.hard = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx;
-    sm.ndc_x = (float*)q;              q += sizeof(float) * ((tile_w + 1) & ~1);
-    sm.ndc_y = (float*)q;              q += sizeof(float) * ((tile_h + 1) & ~1);
-    sm.soft = (unsigned long long*)q;  q += sizeof(unsigned long long) * tpx * p.n_obj;
-    sm.gacc = (unsigned long long*)q;
-    sm.defer_n = &s_wdef_n[warp];
-  }
+  TileSmem sm = tile_smem_layout(smem_raw, tile_w, tile_h, p.n_obj);
+  sm.defer_n = &s_wdef_n[warp];
 
   // ---- tiles no live face touches: background only ---------------------------------------------
   if (n_tiles <= 32 * TILE_MASK_WORDS &&
@@ -927,7 +1392,7 @@ raster_kernel(const RasterParams p) {
     for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_ovf_n = 0; s_hit_n = 0; s_chunk = 0; s_big_n = 0; s_tidx_n = 0; }
+  if (tid == 0) { s_chunk = 0; s_big_n = 0; s_tidx_n = 0; }
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
@@ -1106,218 +1571,10 @@ raster_kernel(const RasterParams p) {
   }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
-  // Rounds of at most OVF_CAP pixels; a resolved pixel carries bit 30 of its count word.
-  for (bool more = true; more;) {
-  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) {
-    const unsigned hi = (unsigned)(sm.soft[i] >> 32);
-    if ((int)(hi & SOFT_CNT_MASK) > p.K && !(hi & SOFT_RESOLVED)) {
-      // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
-      // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
-      // reference's alpha is exactly 1.0f: no selection needed.
-      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
-      if (p.K - weak >= SOFT_STRONG_NEEDED) {
-        sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
-        if (GRAD) sm.gacc[i] = 0ull;
-        atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
-      } else {
-        const int s = atomicAdd(&s_ovf_n, 1);
-        if (s < OVF_CAP) s_ovf[s] = i;
-      }
-    }
-  }
-  __syncthreads();
-  int n_ovf = s_ovf_n;
-  more = n_ovf > OVF_CAP;
-  if (n_ovf > 0) {
-    if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
-    n_ovf = min(n_ovf, OVF_CAP);
-    // candidates: the tile's own face list if it fitted, else the env's whole live list
-    const bool use_tidx = s_tidx_n <= p.tidx_cap;
-    const int n_cand = use_tidx ? s_tidx_n : n_live;
-    // selection buffers alias the (now idle) face list
-    // deterministic order of the overflow list (atomicAdd order is not): sort the small list
-    if (tid == 0) {
-      for (int a = 1; a < n_ovf; ++a) {
-        const int v = s_ovf[a];
-        int b = a - 1;
-        while (b >= 0 && s_ovf[b] > v) { s_ovf[b + 1] = s_ovf[b]; --b; }
-        s_ovf[b + 1] = v;
-      }
-    }
-    __syncthreads();
-    // One pixel at a time:
-    //  A. the faces of this tile whose blur box holds the pixel are compacted into a candidate list,
-    //  B. the candidates are evaluated densely (every thread has work) -> sort key (pz_clipped, face) and factor,
-    //  C. the K-th smallest key is found (rank counting for short lists, 8-bit radix select otherwise),
-    //  D. the factors at or below that key are multiplied (the differentiable kernel re-evaluates those hits
-    //     for their tangent terms).
-    for (int oi = 0; oi < n_ovf; ++oi) {
-      const int slot = s_ovf[oi];
-      if (slot < 0) continue;
-      const int obj = slot / tpx;
-      const int pix = slot - obj * tpx;
-      const int ly = pix / tile_w, lx = pix - ly * tile_w;
-      const int xi = tx0 + lx, yi = ty0 + ly;
-      const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
-      static_assert((size_t)CAND_CAP * 12 <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "candidate buffers must fit the selection buffer");
-      unsigned long long* ckey = (unsigned long long*)sm.list;  // [CAND_CAP]
-      float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its factor
-      __shared__ unsigned long long s_tau;
-      __shared__ int s_hist[256];
-      __shared__ int s_sel[2];
-      if (tid == 0) { s_hit_n = 0; s_sel[0] = 0; }
-      __syncthreads();
-      // A
-      for (int c0 = 0; c0 < n_cand; c0 += OCCL_THREADS) {
-        const int ci = c0 + tid;
-        bool ok = false;
-        int k = 0;
-        if (ci < n_cand) {
-          k = use_tidx ? tidx[ci] : ci;
-          const uint4 rg = __ldg(rng + k);
-          ok = !(xi < (int)(rg.x & 0xffffu) || xi > (int)(rg.x >> 16) || yi < (int)(rg.y & 0xffffu) || yi > (int)(rg.y >> 16)) &&
-               (int)(rg.w >> 30) == obj;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        int base0 = 0;
-        if (lane == 0 && bal) base0 = atomicAdd(&s_hit_n, __popc(bal));
-        base0 = __shfl_sync(0xffffffffu, base0, 0);
-        if (ok) {
-          const int pos = base0 + __popc(bal & ((1u << lane) - 1u));
-          if (pos < CAND_CAP) ((int*)cq)[pos] = k;
-        }
-      }
-      __syncthreads();
-      int nc = s_hit_n;
-      if (nc > CAND_CAP) {
-        if (tid == 0) atomicOr(p.status + env, OCCL_ST_HITCAP);
-        nc = CAND_CAP;
-      }
-      // B
-      int my_hits = 0;
-      for (int i = tid; i < nc; i += OCCL_THREADS) {
-        const int k = ((const int*)cq)[i];
-        const uint4* __restrict__ src = geo + (size_t)k * 4;
-        const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
-        FaceGeo g;
-        g.x0 = __uint_as_float(q0.x); g.y0 = __uint_as_float(q0.y); g.z0 = __uint_as_float(q0.z);
-        g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
-        g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
-        g.area = __uint_as_float(q2.y);
-        const PairResult r = eval_pair(g, px, py);
-        unsigned long long key = ~0ull;
-        float q = 1.0f;
-        if (r.inside || r.dist < p.blur) {
-          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
-          key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
-          q = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
-          ++my_hits;
-        }
-        ckey[i] = key;
-        cq[i] = q;
-      }
-      if (my_hits) atomicAdd(&s_sel[0], my_hits);
-      __syncthreads();
-      const int nh = s_sel[0];
-      int want = min(p.K, nh) - 1;  // 0-based rank of the last key kept
-      // C
-      if (nc <= 512) {
-        for (int a = tid; a < nc; a += OCCL_THREADS) {
-          const unsigned long long ka = ckey[a];
-          int rank = 0;
-          for (int b = 0; b < nc; ++b) rank += ckey[b] < ka;
-          if (rank == want && ka != ~0ull) s_tau = ka;
-        }
-        __syncthreads();
-      } else {
-        unsigned long long prefix = 0ull, mask = 0ull;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-          s_hist[tid] = 0;  // OCCL_THREADS == 256 bins
-          __syncthreads();
-          for (int i = tid; i < nc; i += OCCL_THREADS) {
-            const unsigned long long key = ckey[i];
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(int)((key >> shift) & 255ull)], 1);
-          }
-          __syncthreads();
-          if (warp == 0) {
-            int cnt8[8], sum = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { cnt8[b] = s_hist[lane * 8 + b]; sum += cnt8[b]; }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const int t = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += t;
-            }
-            const int excl = incl - sum;
-            if (want >= excl && want < incl) {
-              int r = want - excl, b = 0;
-              while (r >= cnt8[b]) { r -= cnt8[b]; ++b; }
-              s_sel[0] = lane * 8 + b;
-              s_sel[1] = r;
-            }
-          }
-          __syncthreads();
-          prefix |= (unsigned long long)s_sel[0] << shift;
-          mask |= 255ull << shift;
-          want = s_sel[1];
-          __syncthreads();
-        }
-        if (tid == 0) s_tau = prefix;
-        __syncthreads();
-      }
-      const unsigned long long tau = s_tau;
-      // D
-      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
-      for (int i = tid; i < nc; i += OCCL_THREADS) {
-        const unsigned long long key = ckey[i];
-        if (key > tau) continue;
-        pr = pr * cq[i];
-        if (GRAD) {
-          const int f = (int)(key & 0xffffffffull);
-          const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
-          FaceGeo g;
-          face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, &g);
-          const PairResult r = eval_pair(g, px, py);
-          const float prob = soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
-          const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-          const float4 ta = __ldg(vt + i0), tb = __ldg(vt + i1), tc = __ldg(vt + i2);
-          float ax, ay, bx, by;
-          float4 da, db;
-          if (r.edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = ta; db = tb; }
-          else if (r.edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = ta; db = tc; }
-          else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tb; db = tc; }
-          const float qx = ax + r.t * (bx - ax), qy = ay + r.t * (by - ay);
-          const float sgn = r.inside ? -1.f : 1.f;
-          const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
-          const float wa = 1.f - r.t, wb = r.t;
-          const float kk = prob / p.sigma;
-          g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
-          g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
-        if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
-      }
-      if (lane == 0) { s_red[warp][0] = (double)pr; s_red[warp][1] = (double)g0; s_red[warp][2] = (double)g1; }
-      __syncthreads();
-      if (tid == 0) {
-        float P = 1.0f, G0 = 0.f, G1 = 0.f;
-        for (int w = 0; w < OCCL_WARPS; ++w) { P = P * (float)s_red[w][0]; G0 += (float)s_red[w][1]; G1 += (float)s_red[w][2]; }
-        const unsigned long long old = sm.soft[slot];
-        sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(P);
-        if (GRAD) sm.gacc[(size_t)obj * tpx + pix] = pack2f(G0, G1);
-      }
-      __syncthreads();
-    }
-  }
-  if (more) {
-    __syncthreads();
-    if (tid == 0) s_ovf_n = 0;
-    __syncthreads();
-  }
+  {
+    bool any = false;
+    for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) any |= (int)((unsigned)(sm.soft[i] >> 32) & SOFT_CNT_MASK) > p.K;
+    if (__syncthreads_or(any)) koverflow_resolve<GRAD, TW, TH>(p, env, tile, s_tidx_n);
   }
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
@@ -1730,6 +1987,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   {
     SetupParams sp;
     sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
+    sp.z_clip = c.z_clip; sp.status = out.status;
     sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
     sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
     sp.tile_mask = (uint32_t*)(base + L.tile_mask);

@@ -127,6 +127,7 @@ class Fragments:
     bary: np.ndarray         # (S,S,K,3)
     dists: np.ndarray        # (S,S,K)
     nhits: np.ndarray        # (S,S) hits before the K cut
+    straddles: bool = False  # set by rasterize_clipped
 
 
 def rasterize(vproj, faces, S, blur_radius, K, cull_backfaces=True, perspective_correct=True,
@@ -185,6 +186,30 @@ def rasterize_backward(vproj, faces, frag: Fragments, grad_dists) -> np.ndarray:
 # ------------------------------------------------------------------------------------------------
 # one render of the whole scene from (C, R, T): what reset() and step() share
 # ------------------------------------------------------------------------------------------------
+Z_CLIP = np.float32(0.5)  # MeshRasterizer: z_clip_value = znear / 2 for perspective cameras
+
+
+def clip_cull(vproj, faces, z_clip=Z_CLIP):
+    """The part of pytorch3d renderer/mesh/clip.py::clip_faces that creates no geometry: faces whose three
+    vertices are all nearer than z_clip are removed (case 2); returns (kept face indices, straddles) where
+    straddles=True means some face has 1 or 2 vertices nearer than z_clip (cases 3/4: cut into new triangles by
+    pytorch3d -- not restated; callers must not compare such frames)."""
+    z = vproj[faces, 2]
+    n_clipped = (z < z_clip).sum(axis=1)
+    keep = np.nonzero(n_clipped < 3)[0]
+    return keep, bool(((n_clipped > 0) & (n_clipped < 3)).any())
+
+
+def rasterize_clipped(vproj, faces, S, blur_radius, K, **kw) -> "Fragments":
+    """clip_faces (culling only) -> rasterize_meshes -> face indices mapped back to the unclipped mesh."""
+    keep, straddles = clip_cull(vproj, faces)
+    fr = rasterize(vproj, faces[keep], S, blur_radius, K, **kw)
+    p2f = fr.pix_to_face
+    fr.pix_to_face = np.where(p2f >= 0, keep[np.maximum(p2f, 0)].astype(np.int32) if len(keep) else p2f, p2f).astype(np.int32)
+    fr.straddles = straddles
+    return fr
+
+
 @dataclass
 class RenderOut:
     obs: np.ndarray            # (4,S,S)
@@ -200,6 +225,7 @@ class RenderOut:
     n_visible: np.ndarray      # (n_obj,) px whose nearest scene face belongs to object i
     vproj: np.ndarray          # (V,3)
     frags: list                # per-object K=100 fragments (face ids local to the object)
+    zclip_straddle: bool = False  # a face straddles z_clip: pytorch3d would cut it; this frame is not comparable
 
 
 def render_scene(verts, faces, obj_face_start, obj_vert_start, S, C, R, T, s=PROJ_SCALE,
@@ -212,11 +238,11 @@ def render_scene(verts, faces, obj_face_start, obj_vert_start, S, C, R, T, s=PRO
         f0, f1 = obj_face_start[i], obj_face_start[i + 1]
         of = faces[f0:f1] - v0
         ov = vproj[v0:obj_vert_start[i + 1]]
-        fr = rasterize(ov, of, S, blur, K)                       # silhouette settings :249-255
+        fr = rasterize_clipped(ov, of, S, blur, K)               # silhouette settings :249-255
         frags.append(fr)
         alphas.append(silhouette(fr, sigma))
         nhits.append(fr.nhits)
-        hard = rasterize(ov, of, S, 0.0, 1)                      # object alone, hard coverage
+        hard = rasterize_clipped(ov, of, S, 0.0, 1)              # object alone, hard coverage
         n_cov.append(int((hard.pix_to_face[..., 0] >= 0).sum()))
     alphas = np.stack(alphas)
     occl = np.zeros((S, S), np.float32)
@@ -226,12 +252,13 @@ def render_scene(verts, faces, obj_face_start, obj_vert_start, S, C, R, T, s=PRO
     loss = np.float32(np.sum((occl.astype(np.float64)) ** 2))
     objs = np.sum(alphas.astype(np.float32), axis=0)
     objects_sq = np.float32(np.sum(objs.astype(np.float64) ** 2))
-    scene = rasterize(vproj, faces, S, 0.0, 1)                   # observation settings :267-273
+    scene = rasterize_clipped(vproj, faces, S, 0.0, 1)           # observation settings :267-273
     obs = flat_shade(verts, faces, scene, C, light)
     p2f = scene.pix_to_face[..., 0]
     n_vis = [int(((p2f >= obj_face_start[i]) & (p2f < obj_face_start[i + 1])).sum()) for i in range(n_obj)]
     return RenderOut(obs, alphas, occl, loss, objects_sq, p2f, scene.zbuf[..., 0], scene.bary[..., 0, :],
-                     np.stack(nhits), np.asarray(n_cov), np.asarray(n_vis), vproj, frags)
+                     np.stack(nhits), np.asarray(n_cov), np.asarray(n_vis), vproj, frags,
+                     any(getattr(f, "straddles", False) for f in frags) or bool(getattr(scene, "straddles", False)))
 
 
 class OracleOcclusionEnv:

@@ -441,6 +441,9 @@ def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
     add((1.5, 1.5), (1.7, 1.5), (1.5, 1.8))                           # off screen
     add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 3e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4))  # sub-pixel
     add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4), (c(10) + 3e-4, c(10) + 1e-4))
+    # wholly nearer than z_clip = znear/2: removed by clip_faces (they would cover half the image otherwise)
+    add((-0.9, -0.9), (0.9, -0.9), (0.0, 0.9), z=(0.3, 0.45, 0.4))
+    add((-0.5, -0.5), (0.5, -0.5), (0.0, 0.5), z=(0.2, 0.2, 0.2))
     tris = np.asarray(tris, np.float32)
     verts = tris.reshape(-1, 3)
     faces = np.arange(len(verts), dtype=np.int32).reshape(-1, 3)

@@ -22,13 +22,16 @@ marks = [
     ("exact helpers (eval_pair, bary, seg)", "__device__ __forceinline__ float seg_dist", "// raw SFU approximations"),
     ("div_rn_hoisted / sfu", "// raw SFU approximations", "// clipped-barycentric depth"),
     ("soft_accumulate / hard_update", "__device__ __forceinline__ void soft_accumulate", "// One face against the pixels"),
-    ("raster_face_pixels", "// One face against the pixels", "__device__ __forceinline__ double warp_sum"),
+    ("raster_face_pixels", "// One face against the pixels", "// Tangent terms of one soft hit"),
     ("tile prologue (mask, init)", "raster_kernel(const RasterParams p) {", "// ---- every warp on its own"),
     ("scan + stage", "// ---- every warp on its own", "// process batches of (up to) 32 staged faces"),
     ("batch sort + pass dispatch", "// process batches of (up to) 32 staged faces", "// dense exact-depth pass over this warp"),
     ("deferred depth pass", "// dense exact-depth pass over this warp", "// ---- big faces: the whole CTA"),
-    ("big faces (CTA)", "// ---- big faces: the whole CTA", "// ---- pixels with more than K hits"),
-    ("top-K overflow", "// ---- pixels with more than K hits", "// ---- epilogue: blend, shade"),
+    ("big faces (CTA)", "// ---- big faces: the whole CTA", "// ---- pixels with more than K hits: keep the K nearest"),
+    ("top-K overflow (pre-scan)", "// ---- pixels with more than K hits: keep the K nearest", "// ---- epilogue: blend, shade"),
+    ("top-K overflow: hit-list rounds", "// K-overflow resolution of one tile.", "// ---- pixels with more hits than a round holds"),
+    ("top-K overflow: one-pixel fallback", "// ---- pixels with more hits than a round holds", "// TW, TH: compile-time tile shape"),
+    ("hit_tangent", "// Tangent terms of one soft hit", "__device__ __forceinline__ double warp_sum"),
     ("epilogue", "// ---- epilogue: blend, shade", "// kernel 6: per-env finalisation"),
 ]
 marks = [(n, find(a), find(b)) for n, a, b in marks]
