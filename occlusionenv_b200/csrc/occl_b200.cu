@@ -24,7 +24,15 @@
 
 #include "occl_b200.h"
 
+#ifndef OCCL_THREADS
 #define OCCL_THREADS 256
+#endif
+#ifndef OCCL_TILE_W
+#define OCCL_TILE_W 32         // compile-time tile of the fast instantiation (other shapes: generic kernel)
+#endif
+#ifndef OCCL_TILE_H
+#define OCCL_TILE_H 32
+#endif
 #define OCCL_WARPS (OCCL_THREADS / 32)
 #ifndef SETUP_THREADS
 #define SETUP_THREADS 256     // face_setup_kernel: one CTA per env (1024 measured slower: 1 CTA per SM)
@@ -51,10 +59,10 @@
 #define BIG_FACE_PX 512       // faces covering more tile pixels than this are rasterised by the whole CTA
 #endif
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
-#define CAND_CAP 2048         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
+#define CAND_CAP (256 * OCCL_WARPS)  /* 2048 */         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per round of the one-pixel fallback
-#define HITBUF_CAP 2176       // hits (12 B each) of one selection round: aliases the face list + depth queue
+#define HITBUF_CAP (272 * OCCL_WARPS)  /* 2176 */       // hits (12 B each) of one selection round: aliases the face list + depth queue
 #define WQ_CAP 64             // (slot, face) pairs queued per warp for the dense evaluation of a round
 #define RSLOT_CAP 128         // (pixel, object) slots per selection round (table aliases the big-face records)
 #define REC_WORDS 16
@@ -1240,7 +1248,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       } else {
         unsigned long long prefix = 0ull, mask = 0ull;
         for (int shift = 56; shift >= 0; shift -= 8) {
-          s_hist[tid] = 0;  // OCCL_THREADS == 256 bins
+          for (int b = tid; b < 256; b += OCCL_THREADS) s_hist[b] = 0;
           __syncthreads();
           for (int i = tid; i < nc; i += OCCL_THREADS) {
             const unsigned long long key = ckey[i];
@@ -1345,6 +1353,7 @@ raster_kernel(const RasterParams p) {
       const float inv_qw = 1.0f / (float)qw;
       const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), neg4 = make_float4(-1.f, -1.f, -1.f, -1.f),
                    zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
       for (int i = tid; i < qw * tile_h; i += OCCL_THREADS) {
         const int ly = (int)(((float)i + 0.5f) * inv_qw), lx = (i - ly * qw) * 4;
         const int xi = tx0 + lx, yi = ty0 + ly;
@@ -1358,6 +1367,7 @@ raster_kernel(const RasterParams p) {
         *(float4*)(o + 3 * npix) = neg4;
       }
     } else
+#pragma unroll 1
     for (int i = tid; i < tpx; i += OCCL_THREADS) {
       const int ly = i / tile_w, lx = i - ly * tile_w;
       const int xi = tx0 + lx, yi = ty0 + ly;
@@ -1582,6 +1592,7 @@ raster_kernel(const RasterParams p) {
   double acc_loss = 0.0, acc_obj = 0.0, acc_g0 = 0.0, acc_g1 = 0.0;
   int ncov[OCCL_MAX_OBJ] = {0, 0, 0, 0}, nvis[OCCL_MAX_OBJ] = {0, 0, 0, 0};
   const float inv_tw = 1.0f / (float)tile_w;
+#pragma unroll 1  // a fully unrolled epilogue (4 pixels per thread) is 54 KB of code: it evicts the raster loop from the I-cache
   for (int i = tid; i < tpx; i += OCCL_THREADS) {
     const int ly = (int)(((float)i + 0.5f) * inv_tw), lx = i - ly * tile_w;  // exact for i < 2^21
     const int xi = tx0 + lx, yi = ty0 + ly;
@@ -1843,8 +1854,8 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->tile_w == 0 || c->tile_h == 0) {
     const int S = c->image_size;
     // square tiles split the fewest faces; 32x32 px (1024 px of accumulators) keeps 3 CTAs per SM
-    c->tile_w = S < 32 ? S : 32;
-    c->tile_h = S < 32 ? S : 32;
+    c->tile_w = S < OCCL_TILE_W ? S : OCCL_TILE_W;
+    c->tile_h = S < OCCL_TILE_H ? S : OCCL_TILE_H;
   }
   if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
   if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
@@ -2001,16 +2012,16 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     face_setup_kernel<<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
-  const bool fixed = c.tile_w == 32 && c.tile_h == 32;
+  const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
 #define OCCL_LAUNCH_RASTER(G, W, H)                                                                                   \
   do {                                                                                                                \
     CK(cudaFuncSetAttribute(raster_kernel<G, W, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
     raster_kernel<G, W, H><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
   } while (0)
   if (grad) {
-    if (fixed) OCCL_LAUNCH_RASTER(true, 32, 32); else OCCL_LAUNCH_RASTER(true, 0, 0);
+    if (fixed) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H); else OCCL_LAUNCH_RASTER(true, 0, 0);
   } else {
-    if (fixed) OCCL_LAUNCH_RASTER(false, 32, 32); else OCCL_LAUNCH_RASTER(false, 0, 0);
+    if (fixed) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H); else OCCL_LAUNCH_RASTER(false, 0, 0);
   }
 #undef OCCL_LAUNCH_RASTER
   CK(cudaGetLastError(), "raster_kernel");
