@@ -725,6 +725,21 @@ __device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g
   }
 }
 
+// Rare path of the pixel loop (depth queue full, or the pair went through the reference-order routine): kept out
+// of line so that the loop body stays small (L0 I-cache is ~6 KB).
+__device__ __noinline__ void hard_update_cold(unsigned long long* hard, const uint32_t* rec, int pix, float px, float py,
+                                              float b0, float b1, float b2, bool have_bary) {
+  FaceGeo g;
+  load_geo(rec, &g);
+  if (!have_bary) bary_persp(g, px, py, &b0, &b1, &b2);
+  const float pz = b0 * g.z0 + b1 * g.z1 + b2 * g.z2;
+  if (!(pz < 0.f)) {
+    const unsigned long long key =
+        ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(rec[10] & REC_FIDX_MASK);
+    atomicMin(hard + pix, key);
+  }
+}
+
 // One face against the pixels of its (tile-clipped) blur box; `nlanes` threads stride over them
 // (GROUP_LANES lanes of a warp for a small face -- the other groups of the warp work on other faces in
 // the same instruction stream -- or the whole CTA for a big face).  `active` = this group has a face.
@@ -815,9 +830,7 @@ __device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const 
     if (!inside && dist >= p.blur) continue;
     const int pix = ly * tile_w + lx;
     const float sd = inside ? -dist : dist;
-    float prob;
-    if (need_exact) prob = soft_prob(sd, p.sigma);
-    else prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
+    const float prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
     bool hard_ok = false;
     if (inside) {
       const uint32_t hb = rec[11];
@@ -834,11 +847,7 @@ __device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const 
           queued = true;
         }
       }
-      if (!queued) {
-        FaceGeo g;
-        load_geo(rec, &g);
-        hard_update(sm, g, (int)(w10 & REC_FIDX_MASK), pix, px, py, b0, b1, b2, have_bary);
-      }
+      if (!queued) hard_update_cold(sm.hard, rec, pix, px, py, b0, b1, b2, have_bary);
     }
     if (GRAD) {
       // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
