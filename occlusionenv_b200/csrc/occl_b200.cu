@@ -900,11 +900,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
-}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xffffffffu, v); }
 
 // K-overflow resolution of one tile.  Inlined into the kernel (a non-inlined call measured 5-10 % slower on the
 // main phase: ptxas' register allocation of the barrier-free loop is sensitive to what surrounds it); everything
@@ -1328,7 +1324,9 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
 
 // TW, TH: compile-time tile shape (0 = take it from the parameters); the fixed 32x32 instantiation turns
 // the shared-memory layout and all pixel index arithmetic into constants (register pressure!).
-template <bool GRAD, int TW, int TH>
+// DBG: the parity / debug outputs (per-object alphas, hit counts, pix_to_face, barycentrics) exist only in this
+// instantiation; the production kernel carries no code for them.
+template <bool GRAD, int TW, int TH, bool DBG>
 __global__ void __launch_bounds__(OCCL_THREADS, GRAD ? OCCL_CTAS_GRAD : OCCL_CTAS_FWD)
 raster_kernel(const RasterParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1355,7 +1353,7 @@ raster_kernel(const RasterParams p) {
   if (n_tiles <= 32 * TILE_MASK_WORDS &&
       !((__ldg(p.tile_mask + (size_t)env * TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u)) {
     const size_t npix = (size_t)S * S;
-    const bool debug_out = p.alphas || p.nhits || p.pix_to_face || p.bary;
+    const bool debug_out = DBG && (p.alphas || p.nhits || p.pix_to_face || p.bary);
     if (!debug_out && (tile_w & 3) == 0 && (S & 3) == 0) {
       // 16-byte stores: four pixels of a row per thread and plane
       const int qw = tile_w >> 2;
@@ -1386,11 +1384,11 @@ raster_kernel(const RasterParams p) {
       float* o = p.obs + (size_t)env * 4 * npix + pix;
       o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
       for (int ob = 0; ob < p.n_obj; ++ob) {
-        if (p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
-        if (p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
+        if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
+        if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
       }
-      if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
-      if (p.bary) {
+      if (DBG && p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
+      if (DBG && p.bary) {
         float* bq = p.bary + ((size_t)env * npix + pix) * 3;
         bq[0] = -1.f; bq[1] = -1.f; bq[2] = -1.f;
       }
@@ -1619,11 +1617,11 @@ raster_kernel(const RasterParams p) {
         float* o = p.obs + (size_t)env * 4 * npix + pix;
         o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
         for (int ob = 0; ob < p.n_obj; ++ob) {
-          if (p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
-          if (p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
+          if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
+          if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
         }
-        if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
-        if (p.bary) {
+        if (DBG && p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = -1;
+        if (DBG && p.bary) {
           float* bq = p.bary + ((size_t)env * npix + pix) * 3;
           bq[0] = -1.f; bq[1] = -1.f; bq[2] = -1.f;
         }
@@ -1641,8 +1639,8 @@ raster_kernel(const RasterParams p) {
         A[o] = 1.0f - PR[o];
         const unsigned hi = (unsigned)(w >> 32);
         ncov[o] += (int)(hi >> 31);
-        if (p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
-        if (p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & SOFT_CNT_MASK);
+        if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
+        if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & SOFT_CNT_MASK);
       }
     }
     float occl = 0.f, objs = 0.f;
@@ -1696,8 +1694,8 @@ raster_kernel(const RasterParams p) {
     o[npix] = rgb;
     o[2 * npix] = rgb;
     o[3 * npix] = depth;
-    if (p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = pf;
-    if (p.bary) {
+    if (DBG && p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = pf;
+    if (DBG && p.bary) {
       float* bq = p.bary + ((size_t)env * npix + pix) * 3;
       bq[0] = b0; bq[1] = b1; bq[2] = b2;
     }
@@ -2022,15 +2020,20 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     CK(cudaGetLastError(), "face_setup_kernel");
   }
   const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
-#define OCCL_LAUNCH_RASTER(G, W, H)                                                                                   \
-  do {                                                                                                                \
-    CK(cudaFuncSetAttribute(raster_kernel<G, W, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
-    raster_kernel<G, W, H><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
+#define OCCL_LAUNCH_RASTER(G, W, H, D)                                                                                   \
+  do {                                                                                                                   \
+    CK(cudaFuncSetAttribute(raster_kernel<G, W, H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
+    raster_kernel<G, W, H, D><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
   } while (0)
+  const bool dbg = out.alphas || out.pix_to_face || out.bary || out.nhits;
   if (grad) {
-    if (fixed) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H); else OCCL_LAUNCH_RASTER(true, 0, 0);
+    if (fixed && !dbg) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H, false);
+    else if (fixed) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H, true);
+    else OCCL_LAUNCH_RASTER(true, 0, 0, true);
   } else {
-    if (fixed) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H); else OCCL_LAUNCH_RASTER(false, 0, 0);
+    if (fixed && !dbg) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, false);
+    else if (fixed) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, true);
+    else OCCL_LAUNCH_RASTER(false, 0, 0, true);
   }
 #undef OCCL_LAUNCH_RASTER
   CK(cudaGetLastError(), "raster_kernel");
