@@ -925,8 +925,9 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
   // The reference keeps the K nearest hits by (pz_clipped, face index).  A round takes the next unresolved
   // (pixel, object) slots -- in slot order, as many as their exactly known hit counts fit HITBUF_CAP -- and
   //  1. marks them (bit 29; the product word becomes the write cursor of the slot's segment),
-  //  2. re-evaluates the faces of the tile that touch the round's pixel box with the reference-order routine
-  //     (8 lanes per face) and appends (key, factor) of every hit on a marked slot to its segment,
+  //  2. pairs every marked slot with the faces of the tile whose blur box holds its pixel (per-warp queues),
+  //     re-evaluates the pairs 32 at a time with the reference-order routine and appends (key, factor) of
+  //     every hit to the slot's segment,
   //  3. one warp per slot finds the K-th smallest key by bisection over the key bits (early exit once the
   //     K smallest are separated) and multiplies the factors below it.
   // Slots with more hits than a whole round holds are left to the one-pixel path below.
@@ -934,7 +935,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
     unsigned long long* hkey = (unsigned long long*)sm.list;  // [HITBUF_CAP]
     float* hq = (float*)(hkey + HITBUF_CAP);                    // [HITBUF_CAP]
     static_assert((size_t)HITBUF_CAP * 12 + 4 * OCCL_WARPS * WQ_CAP <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "hit buffer + pair queues must fit the face list");
-    __shared__ int s_rn, s_rb[4], s_wsum[OCCL_WARPS];
+    __shared__ int s_rn, s_todo, s_huge, s_rb[4], s_wsum[OCCL_WARPS];
     __shared__ unsigned s_robj;
     int* s_rslot = (int*)sm.big;                                        // [RSLOT_CAP]  (big faces are done)
     unsigned short* s_roff = (unsigned short*)(s_rslot + RSLOT_CAP);    // [RSLOT_CAP]
@@ -944,9 +945,15 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
     const int s_begin = min(tid * per, n_slots), s_end = min(s_begin + per, n_slots);
     const bool use_tidx = n_tidx <= p.tidx_cap;
     const int n_cand = use_tidx ? n_tidx : n_live;
+    // round counters: set here, and again by thread 0 while a round's selections run (everybody has read them by then)
+    if (tid == 0) { s_rn = 0; s_todo = 0; s_huge = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
+    {
+      bool any = false;
+      for (int i = tid; i < n_slots; i += OCCL_THREADS) any |= (int)((unsigned)(sm.soft[i] >> 32) & SOFT_CNT_MASK) > p.K;
+      if (!__syncthreads_or(any)) return;  // the common tile: no pixel has more than K hits
+    }
     for (;;) {
-      if (tid == 0) { s_rn = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
-      int loc = 0;
+      int loc = 0, todo = 0, huge = 0;
       for (int i = s_begin; i < s_end; ++i) {
         const unsigned hi = (unsigned)(sm.soft[i] >> 32);
         const int cnt = (int)(hi & SOFT_CNT_MASK);
@@ -961,9 +968,14 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
           } else if (cnt <= HITBUF_CAP) {
             loc += cnt;
+            ++todo;
+          } else {
+            ++huge;
           }
         }
       }
+      if (todo) atomicAdd(&s_todo, todo);
+      if (huge) atomicAdd(&s_huge, huge);
       int incl = loc;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -996,7 +1008,12 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       }
       __syncthreads();
       const int rn = p.F <= (1 << 25) ? min(s_rn, RSLOT_CAP) : 0;  // queue entries hold 25 bits of face index
-      if (rn == 0) break;
+      const bool last_round = s_todo == rn;  // nothing left for another round
+      const bool none_huge = s_huge == 0;
+      if (rn == 0) {
+        if (s_todo == 0 && none_huge) return;  // the strong-hit shortcut settled everything
+        break;
+      }
       if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
       // 2. (slot, face) pairs whose blur box holds the slot's pixel: lanes <-> faces of the tile, the round's
       //    slots in turn; the pairs are compacted into a per-warp queue and evaluated 32 at a time with the
@@ -1066,6 +1083,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
         drain(true);
       }
       __syncthreads();
+      if (tid == 0) { s_rn = 0; s_todo = 0; s_huge = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
       // 3. one warp per slot: K-th smallest key, product of the factors up to it
       for (int r = warp; r < rn; r += OCCL_WARPS) {
         const int slot = s_rslot[r];
@@ -1123,6 +1141,10 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
         }
       }
       __syncthreads();
+      if (last_round) {
+        if (none_huge) return;
+        break;
+      }
     }
   }
 
@@ -1588,11 +1610,7 @@ raster_kernel(const RasterParams p) {
   }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
-  {
-    bool any = false;
-    for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) any |= (int)((unsigned)(sm.soft[i] >> 32) & SOFT_CNT_MASK) > p.K;
-    if (__syncthreads_or(any)) koverflow_resolve<GRAD, TW, TH>(p, env, tile, s_tidx_n);
-  }
+  koverflow_resolve<GRAD, TW, TH>(p, env, tile, s_tidx_n);
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
   const size_t npix = (size_t)S * S;
