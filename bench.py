@@ -363,7 +363,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / K,
                 "note": "BatchedOcclusionVecEnv.step(pinned host actions) -> rewards+dones copied to pinned host, stream sync "
                         "every step; observations stay in HBM for the policy, as in the reference (device tensors)"},
-        "gpu_launches": 5 * K,  # pose, project, face_setup, raster, finalize
+        "gpu_launches": 6 * K,  # pose, project, face_setup, raster, raster_clip (cut faces; CTAs leave at once otherwise), finalize
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "raster_kernel", "kernel_ms": raster_ms,
                      "kernel_share_of_step": raster_ms / (ms_total / K),

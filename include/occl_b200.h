@@ -38,8 +38,9 @@ extern "C" {
 #define OCCL_E_SMEM (-3)     /* tile does not fit in shared memory */
 
 /* per-env status bits */
-#define OCCL_ST_ZCLIP 1u       /* a face straddles z_view = z_clip: pytorch3d's clip_faces would cut it (not implemented);
-                                  faces entirely nearer than z_clip are removed, as clip_faces does */
+#define OCCL_ST_ZCLIP 1u       /* the differentiable step met a face that straddles z_view = z_clip: faces are cut there as
+                                  pytorch3d's clip_faces does, but no gradient flows through cut faces (not implemented) */
+#define OCCL_ST_CLIPPED 16u    /* informational: some face was cut at z_clip (clip_faces cases 3/4) */
 #define OCCL_ST_KOVERFLOW 2u   /* some pixel had more than faces_per_pixel hits (handled: nearest-K rule applied) */
 #define OCCL_ST_HITCAP 4u      /* a pixel had more hits than the top-K selection buffer: alpha of that pixel is wrong */
 #define OCCL_ST_OVFCAP 8u      /* reserved (overflowing pixels are handled in rounds; never set) */

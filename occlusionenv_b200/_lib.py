@@ -14,6 +14,7 @@ ST_ZCLIP = 1
 ST_KOVERFLOW = 2
 ST_HITCAP = 4
 ST_OVFCAP = 8
+ST_CLIPPED = 16  # informational: faces were cut at z_clip
 
 _ERR = {-1: "OCCL_E_INVALID (bad argument / unsupported configuration)",
         -2: "OCCL_E_CUDA (CUDA call failed)",

@@ -49,14 +49,14 @@
 #define OCCL_RFP_INLINE __forceinline__
 #endif
 #ifndef BATCH_MIN
-#define BATCH_MIN 16          // a warp rasterises its staged faces once this many are pending
+#define BATCH_MIN 8           // a warp rasterises its staged faces once this many are pending (8..16 measured equal)
 #endif
 #ifndef FACES_PER_PASS
 #define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
 #endif
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
 #ifndef BIG_FACE_PX
-#define BIG_FACE_PX 512       // faces covering more tile pixels than this are rasterised by the whole CTA
+#define BIG_FACE_PX 256       // faces covering more tile pixels than this are rasterised by the whole CTA (64..256 measured equal, 512 3 % slower)
 #endif
 #define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
 #define CAND_CAP (256 * OCCL_WARPS)  /* 2048 */         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
@@ -268,7 +268,7 @@ struct RasterParams {
   int S, n_obj, V, F, K, cull, exact_only;
   int obj_face_start[OCCL_MAX_OBJ + 1];
   int tile_w, tile_h, tiles_x, tiles_y;
-  float blur, bbox_r, sigma, inv_sigma, inv_sigma_log2e;
+  float blur, bbox_r, sigma, inv_sigma, inv_sigma_log2e, z_clip;
   float light[3];
   const float4* vproj;
   const float4* vtan;
@@ -305,7 +305,10 @@ struct RasterParams {
 //   12..14  1/l2 of the edges v0v1, v0v2, v1v2  (fast path only)
 //   15    (tile list only) soft pixel range, tile-local, 8 bits each
 #define REC_FAST 0x80000000u
+#define REC_CLIP 0x40000000u   // the face straddles z_clip: words 0..8 hold the UNCUT vertices (see clip_subtris)
 #define REC_FIDX_MASK 0x0fffffffu
+#define RNG_CLIP 0x80000000u   // same flag in word .z of the range record
+#define KEY_CLIP 0x80000000u   // nearest-face key, low word: the hit is on a cut face; bit 30 = second triangle of the cut
 #define REC_OBJ_SHIFT 28
 #ifndef GROUP_LANES
 #define GROUP_LANES 8         // lanes that rasterise one small face; a warp works on 32/GROUP_LANES faces at once
@@ -456,7 +459,7 @@ __device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const f
   const float zmin = fminf(fminf(g.z0, g.z1), g.z2);
   bool skip = zmax < 0.f;
   skip |= zmax < z_clip;
-  *straddles = !(zmax < z_clip) && zmin < z_clip;
+  *straddles = !(zmax < z_clip) && zmin < z_clip;  // the caller cuts the face; the culls below then apply to the pieces
   skip |= (cull && face_area < 0.f);
   skip |= ((double)face_area <= 1e-8 && (double)face_area >= -1e-8);
   skip |= ((double)zmin < 1e-8);
@@ -509,10 +512,177 @@ __device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, in
 }
 
 // ----------------------------------------------------------------------------------------------
+// z-clip: pytorch3d renderer/mesh/clip.py::clip_faces for the frustum MeshRasterizer builds (z_clip_value only)
+// ----------------------------------------------------------------------------------------------
+// A face with 1 or 2 vertices nearer than z_clip is cut at the plane z = z_clip (in (x_ndc, y_ndc, z_view) space,
+// interpolating x_ndc * z, which is proportional to view-space x):
+//   one vertex p1 nearer : the quadrilateral in front, as t1 = (p4, p2, p5), t2 = (p5, p2, p3)   (neighbours)
+//   two vertices nearer  : the triangle (p1, p4, p5), p1 being the vertex in front
+// p2, p3 follow p1 in the face's own order; p4 / p5 = plane intersections of the edges p1p2 / p1p3.
+// Same operation order as oracle/oracle.py::clip_faces.  conv = barycentrics of the cut triangle's vertices in the
+// uncut face (convert_clipped_rasterization_to_original_faces).
+struct SubTris {
+  int n;
+  FaceGeo g[2];
+  bool live[2];
+  float conv[2][9];
+};
+
+__device__ __forceinline__ float4 clip_cut(const float4 p1, const float4 q, const float zc, float* w_out) {
+  const float w = (p1.z - zc) / (p1.z - q.z);
+  const float a1 = 1.0f - w;
+  const float x = ((p1.x * p1.z) * a1 + (q.x * q.z) * w) / zc;
+  const float y = ((p1.y * p1.z) * a1 + (q.y * q.z) * w) / zc;
+  *w_out = w;
+  return make_float4(x, y, zc, 0.f);
+}
+
+__device__ __noinline__ void clip_subtris(const float4 a, const float4 b, const float4 c, const float zc, const int cull,
+                                          SubTris* out) {
+  const bool c0 = a.z < zc, c1 = b.z < zc, c2 = c.z < zc;
+  const int n = (int)c0 + (int)c1 + (int)c2;
+  out->n = 0;
+  if (n == 0 || n == 3) return;
+  const int i = n == 1 ? (c0 ? 0 : (c1 ? 1 : 2)) : (!c0 ? 0 : (!c1 ? 1 : 2));  // the isolated vertex
+  const float4 p1 = i == 0 ? a : (i == 1 ? b : c);
+  const float4 p2 = i == 0 ? b : (i == 1 ? c : a);
+  const float4 p3 = i == 0 ? c : (i == 1 ? a : b);
+  const int j = (i + 1) % 3, k = (i + 2) % 3;
+  float w2, w3;
+  const float4 p4 = clip_cut(p1, p2, zc, &w2);
+  const float4 p5 = clip_cut(p1, p3, zc, &w3);
+  float e4[3] = {0.f, 0.f, 0.f}, e5[3] = {0.f, 0.f, 0.f}, ei[3] = {0.f, 0.f, 0.f}, ej[3] = {0.f, 0.f, 0.f}, ek[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    ei[t] = t == i ? 1.f : 0.f;
+    ej[t] = t == j ? 1.f : 0.f;
+    ek[t] = t == k ? 1.f : 0.f;
+    e4[t] = t == i ? 1.0f - w2 : (t == j ? w2 : 0.f);
+    e5[t] = t == i ? 1.0f - w3 : (t == k ? w3 : 0.f);
+  }
+  bool unused;
+  if (n == 1) {
+    out->n = 2;
+    out->live[0] = face_geo(p4, p2, p5, cull, 0.f, &out->g[0], &unused);
+    out->live[1] = face_geo(p5, p2, p3, cull, 0.f, &out->g[1], &unused);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      out->conv[0][t] = e4[t]; out->conv[0][3 + t] = ej[t]; out->conv[0][6 + t] = e5[t];
+      out->conv[1][t] = e5[t]; out->conv[1][3 + t] = ej[t]; out->conv[1][6 + t] = ek[t];
+    }
+  } else {
+    out->n = 1;
+    out->live[0] = face_geo(p1, p4, p5, cull, 0.f, &out->g[0], &unused);
+    out->live[1] = false;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      out->conv[0][t] = ei[t]; out->conv[0][3 + t] = e4[t]; out->conv[0][6 + t] = e5[t];
+    }
+  }
+}
+
+// One pixel against a cut face.  Soft (silhouette) and hard (observation) results differ only in the hit rule
+// and in the depth; when both triangles of a cut hit, the one with the smaller distance is kept, the second only
+// if strictly closer (clipped_faces_neighbor_idx rule of the reference's face loop).
+struct ClipPixel {
+  bool soft_hit, soft_inside, hard_hit;
+  float soft_dist, soft_pz;   // squared distance (unsigned), clipped-barycentric depth
+  float hard_pz;              // perspective-correct depth of the nearest... of the chosen triangle
+  int hard_which;
+  float hb0, hb1, hb2;        // barycentrics of the hard hit in the cut triangle
+};
+
+__device__ __noinline__ void eval_clip_pixel(const SubTris* st, const float px, const float py, const float blur,
+                                             const float bbox_r, ClipPixel* o) {
+  o->soft_hit = false; o->hard_hit = false; o->soft_inside = false;
+  o->soft_dist = 0.f; o->soft_pz = 0.f; o->hard_pz = 0.f; o->hard_which = 0; o->hb0 = o->hb1 = o->hb2 = 0.f;
+  float hard_dist = 0.f;
+  for (int t = 0; t < st->n; ++t) {
+    if (!st->live[t]) continue;
+    const FaceGeo& g = st->g[t];
+    const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
+    const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
+    if (px > xhi + bbox_r || px < xlo - bbox_r || py > yhi + bbox_r || py < ylo - bbox_r) continue;
+    const PairResult r = eval_pair(g, px, py);
+    if (r.inside || r.dist < blur) {
+      const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+      if (!(pz < 0.f) && (!o->soft_hit || r.dist < o->soft_dist)) {
+        o->soft_hit = true; o->soft_inside = r.inside; o->soft_dist = r.dist; o->soft_pz = pz;
+      }
+    }
+    if (r.inside && !(px > xhi || px < xlo || py > yhi || py < ylo)) {
+      const float pz = r.b0 * g.z0 + r.b1 * g.z1 + r.b2 * g.z2;
+      if (!(pz < 0.f) && (!o->hard_hit || r.dist < hard_dist)) {
+        o->hard_hit = true; hard_dist = r.dist; o->hard_pz = pz; o->hard_which = t;
+        o->hb0 = r.b0; o->hb1 = r.b1; o->hb2 = r.b2;
+      }
+    }
+  }
+}
+
+// soft result of one (pixel, cut face) pair from the record's uncut vertices (K-overflow paths)
+__device__ __noinline__ bool clip_soft_eval(const uint4* __restrict__ rec, const float px, const float py,
+                                            const float z_clip, const int cull, const float blur, const float bbox_r,
+                                            bool* inside, float* dist, float* pz) {
+  const uint4 q0 = __ldg(rec + 0), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+  SubTris st;
+  clip_subtris(make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), 0.f),
+               make_float4(__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), 0.f),
+               make_float4(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), 0.f), z_clip, cull, &st);
+  ClipPixel cp;
+  eval_clip_pixel(&st, px, py, blur, bbox_r, &cp);
+  *inside = cp.soft_inside; *dist = cp.soft_dist; *pz = cp.soft_pz;
+  return cp.soft_hit;
+}
+
+// K-overflow round: hits of one cut face on the slots of the round (one lane; rare)
+__device__ __noinline__ void clip_round_hits(const uint4* __restrict__ rec, const uint4 rg, const int* s_rslot, const int rn,
+                                             unsigned long long* soft_all, unsigned long long* hkey, float* hq,
+                                             const float* ndc_x, const float* ndc_y, const int tx0, const int ty0,
+                                             const int tile_w, const int tpx, const float z_clip, const int cull,
+                                             const float blur, const float bbox_r, const float sigma) {
+  const int fx0 = (int)(rg.x & 0xffffu) - tx0, fx1 = (int)(rg.x >> 16) - tx0;
+  const int fy0 = (int)(rg.y & 0xffffu) - ty0, fy1 = (int)(rg.y >> 16) - ty0;
+  const int fobj = (int)(rg.w >> 30);
+  const unsigned fidx = __ldg(rec + 2).z & REC_FIDX_MASK;
+  for (int r = 0; r < rn; ++r) {
+    const int slot = s_rslot[r];
+    const int obj = slot / tpx, pix = slot - obj * tpx;
+    const int ly = pix / tile_w, lx = pix - ly * tile_w;
+    if (obj != fobj || lx < fx0 || lx > fx1 || ly < fy0 || ly > fy1) continue;
+    bool inside;
+    float dist, pz;
+    if (!clip_soft_eval(rec, ndc_x[lx], ndc_y[ly], z_clip, cull, blur, bbox_r, &inside, &dist, &pz)) continue;
+    const unsigned pos = atomicAdd((unsigned*)(soft_all + slot), 1u);
+    if (pos < HITBUF_CAP) {
+      hkey[pos] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)fidx;
+      hq[pos] = 1.0f - soft_prob(inside ? -dist : dist, sigma);
+    }
+  }
+}
+
+// epilogue of a pixel whose nearest face is a cut face: barycentrics in the UNCUT face (the reference converts
+// them with the cut triangle's conversion matrix) from the projected vertices of the face
+__device__ __noinline__ void clip_hard_bary(const float4* __restrict__ vp, const int i0, const int i1, const int i2,
+                                            const float z_clip, const int cull, const int which, const float px,
+                                            const float py, float* b0, float* b1, float* b2) {
+  const float4 a = __ldg(vp + i0), b = __ldg(vp + i1), c = __ldg(vp + i2);
+  SubTris st;
+  clip_subtris(a, b, c, z_clip, cull, &st);
+  const int t = which < st.n ? which : 0;
+  float c0, c1, c2;
+  bary_persp(st.g[t], px, py, &c0, &c1, &c2);
+  const float* m = st.conv[t];
+  *b0 = (c0 * m[0] + c1 * m[3]) + c2 * m[6];
+  *b1 = (c0 * m[1] + c1 * m[4]) + c2 * m[7];
+  *b2 = (c0 * m[2] + c1 * m[5]) + c2 * m[8];
+}
+
+// ----------------------------------------------------------------------------------------------
 // kernel 2: per-env face setup + warp-ballot compaction of the live faces
 // ----------------------------------------------------------------------------------------------
 struct SetupParams {
-  int S, V, F, cull, n_obj;
+  int S, V, F, cull, n_obj, grad;
   float z_clip;
   uint32_t* status;
   int obj_face_start[OCCL_MAX_OBJ + 1];
@@ -555,17 +725,33 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
   // mesh order up to the interleaving of concurrently finishing warps (nothing depends on its order).
   for (int base = warp * 32; base < p.F; base += SETUP_THREADS) {
     const int f = base + lane;
-    bool live = false;
+    bool live = false, clipf = false;
     FaceGeo g;
     int sx0 = 0, sx1 = -1, sy0 = 0, sy1 = -1, hx0 = 0, hx1 = -1, hy0 = 0, hy1 = -1;
     if (f < p.F) {
       const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
       bool straddles = false;
-      live = face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, p.z_clip, &g, &straddles);
-      if (straddles) atomicOr(p.status + env, OCCL_ST_ZCLIP);
+      const float4 va = __ldg(vp + i0), vb = __ldg(vp + i1), vc = __ldg(vp + i2);
+      live = face_geo(va, vb, vc, p.cull, p.z_clip, &g, &straddles);
+      float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
+      float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
+      if (straddles) {
+        // cut at z = z_clip: the record keeps the uncut vertices, its pixel ranges are those of the cut polygon
+        atomicOr(p.status + env, p.grad ? (OCCL_ST_ZCLIP | OCCL_ST_CLIPPED) : OCCL_ST_CLIPPED);  // no gradient through cut faces
+        SubTris st;
+        clip_subtris(va, vb, vc, p.z_clip, p.cull, &st);
+        live = false;
+        xlo = ylo = 3.0e38f; xhi = yhi = -3.0e38f;
+        for (int t = 0; t < st.n; ++t) {
+          if (!st.live[t]) continue;
+          live = true;
+          const FaceGeo& q = st.g[t];
+          xlo = fminf(xlo, fminf(fminf(q.x0, q.x1), q.x2)); xhi = fmaxf(xhi, fmaxf(fmaxf(q.x0, q.x1), q.x2));
+          ylo = fminf(ylo, fminf(fminf(q.y0, q.y1), q.y2)); yhi = fmaxf(yhi, fmaxf(fmaxf(q.y0, q.y1), q.y2));
+        }
+        clipf = live;
+      }
       if (live) {
-        const float xlo = fminf(fminf(g.x0, g.x1), g.x2), xhi = fmaxf(fmaxf(g.x0, g.x1), g.x2);
-        const float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
         ndc_range_to_pixels(tab, xlo - p.bbox_r, xhi + p.bbox_r, S, &sx0, &sx1);
         ndc_range_to_pixels(tab, ylo - p.bbox_r, yhi + p.bbox_r, S, &sy0, &sy1);
         live = sx0 <= sx1 && sy0 <= sy1;  // faces whose blur box misses every pixel centre
@@ -590,7 +776,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       const float zmax = fmaxf(fmaxf(g.z0, g.z1), g.z2), zmin = fminf(fminf(g.z0, g.z1), g.z2);
       const float cmax = fmaxf(fmaxf(fmaxf(fabsf(g.x0), fabsf(g.x1)), fabsf(g.x2)),
                                fmaxf(fmaxf(fabsf(g.y0), fabsf(g.y1)), fabsf(g.y2)));
-      const bool fast = g.area >= 9.094947e-13f /*2^-40*/ && g.area <= 1024.f && zmin >= 9.765625e-4f && zmax <= 1024.f &&
+      const bool fast = !clipf && g.area >= 9.094947e-13f /*2^-40*/ && g.area <= 1024.f && zmin >= 9.765625e-4f && zmax <= 1024.f &&
                         cmax <= 4.0f && l01 > 1e-8f && l02 > 1e-8f && l12 > 1e-8f;
       uint4 q0, q1, q2, q3;
       q0 = make_uint4(__float_as_uint(g.x0), __float_as_uint(g.y0), __float_as_uint(g.z0), __float_as_uint(g.x1));
@@ -600,7 +786,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       for (int i = 1; i < OCCL_MAX_OBJ; ++i)
         if (i < p.n_obj && f >= p.obj_face_start[i]) obj = i;
       q2 = make_uint4(__float_as_uint(g.z2), __float_as_uint(g.area),
-                      (uint32_t)f | (obj << REC_OBJ_SHIFT) | (fast ? REC_FAST : 0u), 0u);
+                      (uint32_t)f | (obj << REC_OBJ_SHIFT) | (fast ? REC_FAST : 0u) | (clipf ? REC_CLIP : 0u), 0u);
       if (p.n_tiles <= 32 * TILE_MASK_WORDS) {
         // exact for these small integers: (i + 0.5) / t never lands within 0.5/t of an integer
         const int tx_lo = (int)(((float)sx0 + 0.5f) * p.inv_tile_w), tx_hi = (int)(((float)sx1 + 0.5f) * p.inv_tile_w);
@@ -621,7 +807,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
                           __ldg(faces + 3 * f + 2), p.light, __ldg(cam + 12), __ldg(cam + 13), __ldg(cam + 14));
       }
       rng[slot] = make_uint4((uint32_t)sx0 | ((uint32_t)sx1 << 16), (uint32_t)sy0 | ((uint32_t)sy1 << 16),
-                             (uint32_t)hx0 | ((uint32_t)hx1 << 16), (uint32_t)hy0 | ((uint32_t)hy1 << 16) | (obj << 30));
+                             (uint32_t)hx0 | ((uint32_t)hx1 << 16) | (clipf ? RNG_CLIP : 0u),
+                             (uint32_t)hy0 | ((uint32_t)hy1 << 16) | (obj << 30));
     }
   }
   __syncthreads();
@@ -722,6 +909,70 @@ __device__ __forceinline__ void hard_update(const TileSmem& sm, const FaceGeo& g
     const unsigned long long key =
         ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(unsigned)fidx;
     atomicMin(sm.hard + pix, key);
+  }
+}
+
+// A cut face (REC_CLIP) against the pixels of its tile-clipped blur box, by one warp (rare: geometry within
+// z_clip = znear/2 of the camera; never on the fast path).
+__device__ __noinline__ void raster_clip_record(const uint4* __restrict__ rec, const int cx0, const int cx1, const int cy0,
+                                                const int cy1, unsigned long long* soft_all, unsigned long long* hard,
+                                                const float* ndc_x, const float* ndc_y, const int tile_w, const int tpx,
+                                                const float z_clip, const int cull, const float blur, const float bbox_r,
+                                                const float inv_sigma_log2e, const int lane) {
+  const uint4 q0 = __ldg(rec + 0), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+  SubTris st;
+  clip_subtris(make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), 0.f),
+               make_float4(__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), 0.f),
+               make_float4(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), 0.f), z_clip, cull, &st);
+  const uint32_t w10 = q2.z;
+  unsigned long long* soft = soft_all + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx;
+  const int w = cx1 - cx0 + 1, n = w * (cy1 - cy0 + 1);
+  for (int i = lane; i < n; i += 32) {
+    const int ry = i / w, lx = cx0 + (i - ry * w), ly = cy0 + ry;
+    const int pix = ly * tile_w + lx;
+    ClipPixel cp;
+    eval_clip_pixel(&st, ndc_x[lx], ndc_y[ly], blur, bbox_r, &cp);
+    if (cp.soft_hit) {
+      const float sd = cp.soft_inside ? -cp.soft_dist : cp.soft_dist;
+      const float prob = rcp_approx(1.0f + ex2_approx(sd * inv_sigma_log2e));
+      soft_accumulate(soft + pix, 1.0f - prob, cp.hard_hit);
+    }
+    if (cp.hard_hit) {
+      const unsigned low = (w10 & REC_FIDX_MASK) | KEY_CLIP | ((unsigned)cp.hard_which << 30);
+      atomicMin(hard + pix, ((unsigned long long)__float_as_uint(cp.hard_pz) << 32) | (unsigned long long)low);
+    }
+  }
+}
+
+// Clip phase of a tile (after the barrier-free phase; only in envs where the setup kernel cut a face): the warps
+// look through the faces of the tile for cut ones and rasterise each warp-wide.
+__device__ __noinline__ void clip_phase(const uint4* __restrict__ geo, const uint4* __restrict__ rng,
+                                        const int* __restrict__ tidx, const int n_cand, const bool use_tidx, const int tx0,
+                                        const int ty0, const int tx1, const int ty1, unsigned long long* soft_all,
+                                        unsigned long long* hard, const float* ndc_x, const float* ndc_y, const int tile_w,
+                                        const int tpx, const float z_clip, const int cull, const float blur,
+                                        const float bbox_r, const float inv_sigma_log2e) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = warp * 32; c0 < n_cand; c0 += OCCL_THREADS) {
+    const int ci = c0 + lane;
+    bool cut = false;
+    int k = 0, cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+    if (ci < n_cand) {
+      k = use_tidx ? tidx[ci] : ci;
+      const uint4 rg = __ldg(rng + k);
+      cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
+      cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
+      cut = (rg.z & RNG_CLIP) && cx0 <= cx1 && cy0 <= cy1;
+    }
+    for (unsigned cb = __ballot_sync(0xffffffffu, cut); cb;) {
+      const int bl = __ffs(cb) - 1;
+      cb &= cb - 1;
+      const int kb = __shfl_sync(0xffffffffu, k, bl);
+      const int bx0 = __shfl_sync(0xffffffffu, cx0, bl), bx1 = __shfl_sync(0xffffffffu, cx1, bl);
+      const int by0 = __shfl_sync(0xffffffffu, cy0, bl), by1 = __shfl_sync(0xffffffffu, cy1, bl);
+      raster_clip_record(geo + (size_t)kb * 4, bx0 - tx0, bx1 - tx0, by0 - ty0, by1 - ty0, soft_all, hard, ndc_x, ndc_y,
+                         tile_w, tpx, z_clip, cull, blur, bbox_r, inv_sigma_log2e, lane);
+    }
   }
 }
 
@@ -905,7 +1156,7 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xff
 // K-overflow resolution of one tile.  Inlined into the kernel (a non-inlined call measured 5-10 % slower on the
 // main phase: ptxas' register allocation of the barrier-free loop is sensitive to what surrounds it); everything
 // is recomputed here so that nothing extra stays live across the caller's main phase.
-template <bool GRAD, int TW, int TH>
+template <bool GRAD, int TW, int TH, bool CLIPF>
 __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const int env, const int tile, const int n_tidx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
@@ -1061,7 +1312,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             k = use_tidx ? tidx[ci] : ci;
             rg = __ldg(rng + k);
             ok = !(bx1 < (int)(rg.x & 0xffffu) || bx0 > (int)(rg.x >> 16) || by1 < (int)(rg.y & 0xffffu) || by0 > (int)(rg.y >> 16)) &&
-                 ((robj >> (rg.w >> 30)) & 1u);
+                 ((robj >> (rg.w >> 30)) & 1u) && !(CLIPF && (rg.z & RNG_CLIP));  // cut faces: separate pass below
           }
           if (!__any_sync(0xffffffffu, ok)) continue;
           const int fx0 = (int)(rg.x & 0xffffu) - tx0, fx1 = (int)(rg.x >> 16) - tx0;
@@ -1081,6 +1332,17 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
           }
         }
         drain(true);
+        // cut faces (z-clip) of the tile, if the env has any: one lane per face, every slot of the round (rare)
+        if (CLIPF) {
+          for (int ci = tid; ci < n_cand; ci += OCCL_THREADS) {
+            const int k = use_tidx ? tidx[ci] : ci;
+            const uint4 rg = __ldg(rng + k);
+            if ((rg.z & RNG_CLIP) && ((robj >> (rg.w >> 30)) & 1u) &&
+                !(bx1 < (int)(rg.x & 0xffffu) || bx0 > (int)(rg.x >> 16) || by1 < (int)(rg.y & 0xffffu) || by0 > (int)(rg.y >> 16)))
+              clip_round_hits(geo + (size_t)k * 4, rg, s_rslot, rn, sm.soft, hkey, hq, sm.ndc_x, sm.ndc_y, tx0, ty0, tile_w, tpx,
+                              p.z_clip, p.cull, p.blur, p.bbox_r, p.sigma);
+          }
+        }
       }
       __syncthreads();
       if (tid == 0) { s_rn = 0; s_todo = 0; s_huge = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
@@ -1247,13 +1509,21 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
         g.x1 = __uint_as_float(q0.w); g.y1 = __uint_as_float(q1.x); g.z1 = __uint_as_float(q1.y);
         g.x2 = __uint_as_float(q1.z); g.y2 = __uint_as_float(q1.w); g.z2 = __uint_as_float(q2.x);
         g.area = __uint_as_float(q2.y);
-        const PairResult r = eval_pair(g, px, py);
+        bool hit, inside;
+        float dist, pz = 0.f;
+        if (CLIPF && (q2.z & REC_CLIP)) {
+          hit = clip_soft_eval(src, px, py, p.z_clip, p.cull, p.blur, p.bbox_r, &inside, &dist, &pz);
+        } else {
+          const PairResult r = eval_pair(g, px, py);
+          inside = r.inside; dist = r.dist;
+          hit = r.inside || r.dist < p.blur;
+          if (hit) pz = pz_clipped(g, r.b0, r.b1, r.b2);
+        }
         unsigned long long key = ~0ull;
         float q = 1.0f;
-        if (r.inside || r.dist < p.blur) {
-          const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
+        if (hit) {
           key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
-          q = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+          q = 1.0f - soft_prob(inside ? -dist : dist, p.sigma);
           ++my_hits;
         }
         ckey[i] = key;
@@ -1348,15 +1618,13 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
 // the shared-memory layout and all pixel index arithmetic into constants (register pressure!).
 // DBG: the parity / debug outputs (per-object alphas, hit counts, pix_to_face, barycentrics) exist only in this
 // instantiation; the production kernel carries no code for them.
-template <bool GRAD, int TW, int TH, bool DBG>
-__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? OCCL_CTAS_GRAD : OCCL_CTAS_FWD)
-raster_kernel(const RasterParams p) {
+// CLIPF: the code for faces cut at z_clip (clip_faces cases 3/4) exists only in this instantiation; it runs in
+// raster_clip_kernel, for the (rare) envs in which the setup kernel cut a face.
+template <bool GRAD, int TW, int TH, bool DBG, bool CLIPF>
+__device__ __forceinline__ void raster_tile(const RasterParams& p, const int env, const int tile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_tiles = p.tiles_x * p.tiles_y;
-  const int env = blockIdx.x / n_tiles;
-  const int tile = blockIdx.x - env * n_tiles;
-  if (p.env_mask && !p.env_mask[env]) return;
   const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
   const int tx0 = (tile % p.tiles_x) * tile_w;
   const int ty0 = (tile / p.tiles_x) * tile_h;
@@ -1482,12 +1750,13 @@ raster_kernel(const RasterParams p) {
           const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
           const uint4* __restrict__ src = geo + (size_t)k * 4;
           uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
-          int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)(rg.z >> 16), tx1) - tx0;
+          int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)((rg.z >> 16) & 0x7fffu), tx1) - tx0;
           int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)((rg.w >> 16) & 0x3fffu), ty1) - ty0;
           if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
           q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
           q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
                  ((uint32_t)(cy1 - ty0) << 24);
+          if (CLIPF && (rg.z & RNG_CLIP)) q3.w = 1u;  // cut face (z-clip): empty box here, rasterised by the clip phase
           uint4* dst = (uint4*)(wbuf + slot * REC_WORDS);
           dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
         }
@@ -1609,8 +1878,22 @@ raster_kernel(const RasterParams p) {
     if (nb) __syncthreads();
   }
 
+  // ---- cut faces (z-clip) ------------------------------------------------------------------------
+  if (CLIPF) {
+    // everything is recomputed from (env, tile): nothing extra may stay live across the main phase
+    const int n_t = s_tidx_n;
+    const bool use_t = n_t <= p.tidx_cap;
+    const int ctx0 = (tile % p.tiles_x) * tile_w, cty0 = (tile / p.tiles_x) * tile_h;
+    const TileSmem csm = tile_smem_layout(smem_raw, tile_w, tile_h, p.n_obj);
+    clip_phase(p.geo + (size_t)env * p.F * 4, p.rng + (size_t)env * p.F,
+               p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap, use_t ? n_t : p.n_live[env], use_t, ctx0, cty0,
+               ctx0 + tile_w - 1, cty0 + tile_h - 1, csm.soft, csm.hard, csm.ndc_x, csm.ndc_y, tile_w, tile_w * tile_h, p.z_clip,
+               p.cull, p.blur, p.bbox_r, p.inv_sigma_log2e);
+    __syncthreads();
+  }
+
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
-  koverflow_resolve<GRAD, TW, TH>(p, env, tile, s_tidx_n);
+  koverflow_resolve<GRAD, TW, TH, CLIPF>(p, env, tile, s_tidx_n);
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
   const size_t npix = (size_t)S * S;
@@ -1693,16 +1976,21 @@ raster_kernel(const RasterParams p) {
     int pf = -1;
     float b0 = -1.f, b1 = -1.f, b2 = -1.f;
     if (key != ~0ull) {
-      pf = (int)(unsigned)(key & 0xffffffffull);
+      const unsigned klow = (unsigned)(key & 0xffffffffull);
+      pf = (int)(klow & REC_FIDX_MASK);
       depth = __uint_as_float((unsigned)(key >> 32));
       nvis[obj_of_face(p, pf)] += 1;
       const int i0 = __ldg(faces + 3 * pf + 0), i1 = __ldg(faces + 3 * pf + 1), i2 = __ldg(faces + 3 * pf + 2);
+      if (CLIPF && (klow & KEY_CLIP)) {
+        clip_hard_bary(vp, i0, i1, i2, p.z_clip, p.cull, (int)((klow >> 30) & 1u), sm.ndc_x[lx], sm.ndc_y[ly], &b0, &b1, &b2);
+      } else {
       const float4 a = __ldg(vp + i0), b = __ldg(vp + i1), c = __ldg(vp + i2);
       FaceGeo g;
       g.x0 = a.x; g.y0 = a.y; g.z0 = a.z; g.x1 = b.x; g.y1 = b.y; g.z1 = b.z; g.x2 = c.x; g.y2 = c.y; g.z2 = c.z;
       const float e = (g.x2 - g.x0) * (g.y1 - g.y0) - (g.y2 - g.y0) * (g.x1 - g.x0);
       g.area = (float)((double)e + 1e-8);
       bary_persp(g, sm.ndc_x[lx], sm.ndc_y[ly], &b0, &b1, &b2);
+      }
       const float2 sh = __ldg(p.shade + (size_t)env * p.F + pf);
       const float texel = (b0 + b1) + b2;
       rgb = sh.x * texel + sh.y;
@@ -1739,6 +2027,33 @@ raster_kernel(const RasterParams p) {
       for (int o = 0; o < OCCL_MAX_OBJ; ++o) { out.ncov[o] += s_redi[w][o]; out.nvis[o] += s_redi[w][OCCL_MAX_OBJ + o]; }
     }
     p.partials[(size_t)env * n_tiles + tile] = out;
+  }
+}
+
+
+// One CTA per (env, tile).  Envs in which a face was cut at z_clip are left to raster_clip_kernel.
+template <bool GRAD, int TW, int TH, bool DBG>
+__global__ void __launch_bounds__(OCCL_THREADS, GRAD ? OCCL_CTAS_GRAD : OCCL_CTAS_FWD)
+raster_kernel(const RasterParams p) {
+  const int n_tiles = p.tiles_x * p.tiles_y;
+  const int env = blockIdx.x / n_tiles;
+  const int tile = blockIdx.x - env * n_tiles;
+  if (p.env_mask && !p.env_mask[env]) return;
+  if (*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED) return;
+  raster_tile<GRAD, TW, TH, DBG, false>(p, env, tile);
+}
+
+// One CTA per env, only for envs with cut faces (camera within z_clip = znear/2 of the geometry): the tiles in
+// turn, with the clip-capable instantiation of the tile rasteriser.  Everywhere else the CTA leaves at once.
+template <bool GRAD>
+__global__ void __launch_bounds__(OCCL_THREADS) raster_clip_kernel(const RasterParams p) {
+  const int env = blockIdx.x;
+  if (p.env_mask && !p.env_mask[env]) return;
+  if (!(*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED)) return;
+  const int n_tiles = p.tiles_x * p.tiles_y;
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    raster_tile<GRAD, 0, 0, true, true>(p, env, tile);
+    __syncthreads();
   }
 }
 
@@ -2000,7 +2315,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.tile_w = c.tile_w; p.tile_h = c.tile_h;
   p.tiles_x = (c.image_size + c.tile_w - 1) / c.tile_w;
   p.tiles_y = (c.image_size + c.tile_h - 1) / c.tile_h;
-  p.blur = c.blur_radius; p.bbox_r = sqrtf(c.blur_radius); p.sigma = c.sigma;
+  p.blur = c.blur_radius; p.bbox_r = sqrtf(c.blur_radius); p.sigma = c.sigma; p.z_clip = c.z_clip;
   p.inv_sigma = 1.0f / c.sigma;
   p.inv_sigma_log2e = (float)(1.4426950408889634 / (double)c.sigma);
   p.exact_only = c.debug_exact;
@@ -2023,7 +2338,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   {
     SetupParams sp;
     sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
-    sp.z_clip = c.z_clip; sp.status = out.status;
+    sp.z_clip = c.z_clip; sp.status = out.status; sp.grad = grad;
     sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
     sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
     sp.tile_mask = (uint32_t*)(base + L.tile_mask);
@@ -2052,6 +2367,14 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     if (fixed && !dbg) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, false);
     else if (fixed) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, true);
     else OCCL_LAUNCH_RASTER(false, 0, 0, true);
+  }
+  // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile
+  if (grad) {
+    CK(cudaFuncSetAttribute(raster_clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    raster_clip_kernel<true><<<(unsigned)n, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    CK(cudaFuncSetAttribute(raster_clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    raster_clip_kernel<false><<<(unsigned)n, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
   }
 #undef OCCL_LAUNCH_RASTER
   CK(cudaGetLastError(), "raster_kernel");

@@ -261,12 +261,16 @@ static int eval_pixel_face(const face_t* fc, float px, float py, float blur_radi
   return 1;
 }
 
-/* RasterizeMeshesNaiveCpu for one mesh.  vproj: (V,3) = (x_ndc, y_ndc, z_view); faces (F,3).
- * Outputs are (S,S,K) [bary (S,S,K,3)], -1 filled.  nhits (S,S), optional: hits before the K cut. */
-void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int S,
-                           float blur_radius, int K, int persp, int clip_bary, int cull,
-                           int32_t* pix_to_face, float* zbuf, float* bary, float* dists,
-                           int32_t* nhits) {
+/* RasterizeMeshesNaiveCpu for one mesh, on explicit face vertices: face_verts (F,3,3) = (x_ndc, y_ndc, z_view).
+ * neighbor (F) or NULL: clipped_faces_neighbor_idx of pytorch3d renderer/mesh/clip.py -- the two triangles a
+ * face with one vertex nearer than z_clip is cut into name each other; when both hit a pixel only the one with
+ * the smaller |dist| is kept (the later face replaces the earlier only if strictly closer), as in the face loop
+ * of rasterize_meshes_cpu.cpp.  Outputs are (S,S,K) [bary (S,S,K,3)], -1 filled.  nhits (S,S), optional: hits
+ * before the K cut. */
+void occl_oracle_rasterize_fv(const float* face_verts, const int32_t* neighbor, int F, int S,
+                              float blur_radius, int K, int persp, int clip_bary, int cull,
+                              int32_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                              int32_t* nhits) {
   const size_t npix = (size_t)S * S;
   for (size_t i = 0; i < npix * K; ++i) {
     pix_to_face[i] = -1;
@@ -277,12 +281,7 @@ void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int 
 
   const float bbox_r = sqrtf(blur_radius);
   face_t* fc = (face_t*)malloc(sizeof(face_t) * (size_t)(F > 0 ? F : 1));
-  for (int f = 0; f < F; ++f) {
-    float fv[9];
-    for (int k = 0; k < 3; ++k)
-      for (int c = 0; c < 3; ++c) fv[k * 3 + c] = vproj[faces[f * 3 + k] * 3 + c];
-    setup_face(fv, bbox_r, cull, &fc[f]);
-  }
+  for (int f = 0; f < F; ++f) setup_face(face_verts + (size_t)f * 9, bbox_r, cull, &fc[f]);
   size_t cap = 4096;
   hit_t* q = (hit_t*)malloc(sizeof(hit_t) * cap);
 
@@ -295,6 +294,15 @@ void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int 
         hit_t h;
         if (!eval_pixel_face(&fc[f], xf, yf, blur_radius, persp, clip_bary, &h)) continue;
         h.f = f;
+        if (neighbor && neighbor[f] >= 0) {
+          int found = -1;
+          for (size_t i = 0; i < n; ++i)
+            if (q[i].f == neighbor[f]) { found = (int)i; break; }
+          if (found >= 0) {
+            if (fabsf(h.dist) < fabsf(q[found].dist)) q[found] = h;
+            continue;
+          }
+        }
         if (n == cap) {
           cap *= 2;
           q = (hit_t*)realloc(q, sizeof(hit_t) * cap);
@@ -319,6 +327,19 @@ void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int 
   }
   free(q);
   free(fc);
+}
+
+/* RasterizeMeshesNaiveCpu for one mesh.  vproj: (V,3) = (x_ndc, y_ndc, z_view); faces (F,3). */
+void occl_oracle_rasterize(const float* vproj, const int32_t* faces, int F, int S,
+                           float blur_radius, int K, int persp, int clip_bary, int cull,
+                           int32_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                           int32_t* nhits) {
+  float* fv = (float*)malloc(sizeof(float) * 9 * (size_t)(F > 0 ? F : 1));
+  for (int f = 0; f < F; ++f)
+    for (int k = 0; k < 3; ++k)
+      for (int c = 0; c < 3; ++c) fv[(size_t)f * 9 + k * 3 + c] = vproj[faces[f * 3 + k] * 3 + c];
+  occl_oracle_rasterize_fv(fv, NULL, F, S, blur_radius, K, persp, clip_bary, cull, pix_to_face, zbuf, bary, dists, nhits);
+  free(fv);
 }
 
 /* ------------------------------------------------------------------------------------------ */

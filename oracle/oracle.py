@@ -189,24 +189,100 @@ def rasterize_backward(vproj, faces, frag: Fragments, grad_dists) -> np.ndarray:
 Z_CLIP = np.float32(0.5)  # MeshRasterizer: z_clip_value = znear / 2 for perspective cameras
 
 
-def clip_cull(vproj, faces, z_clip=Z_CLIP):
-    """The part of pytorch3d renderer/mesh/clip.py::clip_faces that creates no geometry: faces whose three
-    vertices are all nearer than z_clip are removed (case 2); returns (kept face indices, straddles) where
-    straddles=True means some face has 1 or 2 vertices nearer than z_clip (cases 3/4: cut into new triangles by
-    pytorch3d -- not restated; callers must not compare such frames)."""
-    z = vproj[faces, 2]
-    n_clipped = (z < z_clip).sum(axis=1)
-    keep = np.nonzero(n_clipped < 3)[0]
-    return keep, bool(((n_clipped > 0) & (n_clipped < 3)).any())
+def rasterize_fv(face_verts, neighbor, S, blur_radius, K, cull_backfaces=True, perspective_correct=True,
+                 clip_barycentric_coords=None) -> Fragments:
+    """rasterize() on explicit face vertices (F,3,3) with pytorch3d's clipped_faces_neighbor_idx rule."""
+    if clip_barycentric_coords is None:
+        clip_barycentric_coords = blur_radius > 0
+    fv = np.ascontiguousarray(face_verts, np.float32).reshape(-1, 9)
+    F = fv.shape[0]
+    nb = None if neighbor is None else np.ascontiguousarray(neighbor, np.int32)
+    p2f = np.empty((S, S, K), np.int32)
+    zb = np.empty((S, S, K), np.float32)
+    ba = np.empty((S, S, K, 3), np.float32)
+    di = np.empty((S, S, K), np.float32)
+    nh = np.zeros((S, S), np.int32)
+    lib().occl_oracle_rasterize_fv(_fp(fv), _ip(nb) if nb is not None else None, F, S, ctypes.c_float(float(blur_radius)),
+                                   K, int(perspective_correct), int(clip_barycentric_coords), int(cull_backfaces),
+                                   _ip(p2f), _fp(zb), _fp(ba), _fp(di), _ip(nh))
+    return Fragments(p2f, zb, ba, di, nh)
+
+
+def clip_faces(face_verts, z_clip=Z_CLIP):
+    """pytorch3d renderer/mesh/clip.py::clip_faces for the frustum MeshRasterizer builds (only z_clip_value set,
+    perspective_correct=True, cull=False), on face_verts (F,3,3) = (x_ndc, y_ndc, z_view).  Per face, by the number
+    of vertices with z < z_clip:  0 -> kept;  3 -> removed;  1 -> the quadrilateral in front of the plane, as the
+    two triangles t1 = (p4, p2, p5), t2 = (p5, p2, p3);  2 -> the triangle (p1, p4, p5).  p1 is the isolated vertex,
+    p2, p3 follow it in the face's own order, p4 / p5 are the intersections of the edges p1p2 / p1p3 with z = z_clip:
+        w = (p1.z - z_clip) / (p1.z - p.z);   xy = (p1.xy * p1.z * (1 - w) + p.xy * p.z * w) / z_clip
+    (interpolated in view space -- x_ndc * z is s * x_view -- and projected again).  [P3D-recalled; the operation
+    order of the interpolation is this restatement's choice: parity unpinned.]
+    Returns (clipped face_verts (Fc,3,3), clipped->unclipped index (Fc,), neighbour index (Fc,) or -1,
+    barycentric conversion (Fc,3,3): rows = barycentrics of the clipped face's vertices in the unclipped face)."""
+    fv = np.ascontiguousarray(face_verts, np.float32)
+    zc = np.float32(z_clip)
+    out_v, out_idx, out_nb, out_conv = [], [], [], []
+    eye = np.eye(3, dtype=np.float32)
+    one = np.float32(1.0)
+    for f in range(fv.shape[0]):
+        v = fv[f]
+        behind = v[:, 2] < zc
+        n = int(behind.sum())
+        if n == 0:
+            out_v.append(v); out_idx.append(f); out_nb.append(-1); out_conv.append(eye)
+            continue
+        if n == 3:
+            continue
+        i = int(np.argmax(behind)) if n == 1 else int(np.argmax(~behind))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        p1, p2, p3 = v[i], v[j], v[k]
+
+        def cut(p):
+            w = np.float32((p1[2] - zc) / (p1[2] - p[2]))
+            a1 = np.float32(one - w)
+            x = np.float32(np.float32(np.float32(p1[0] * p1[2]) * a1 + np.float32(np.float32(p[0] * p[2]) * w)) / zc)
+            y = np.float32(np.float32(np.float32(p1[1] * p1[2]) * a1 + np.float32(np.float32(p[1] * p[2]) * w)) / zc)
+            return np.array([x, y, zc], np.float32), w
+
+        p4, w2 = cut(p2)
+        p5, w3 = cut(p3)
+        b4 = np.zeros(3, np.float32); b4[i] = one - w2; b4[j] = w2
+        b5 = np.zeros(3, np.float32); b5[i] = one - w3; b5[k] = w3
+        if n == 1:
+            base = len(out_v)
+            out_v += [np.stack([p4, p2, p5]), np.stack([p5, p2, p3])]
+            out_idx += [f, f]
+            out_nb += [base + 1, base]
+            out_conv += [np.stack([b4, eye[j], b5]), np.stack([b5, eye[j], eye[k]])]
+        else:
+            out_v.append(np.stack([p1, p4, p5])); out_idx.append(f); out_nb.append(-1)
+            out_conv.append(np.stack([eye[i], b4, b5]))
+    if not out_v:
+        return (np.zeros((0, 3, 3), np.float32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 3, 3), np.float32))
+    return (np.stack(out_v).astype(np.float32), np.asarray(out_idx, np.int32), np.asarray(out_nb, np.int32),
+            np.stack(out_conv).astype(np.float32))
 
 
 def rasterize_clipped(vproj, faces, S, blur_radius, K, **kw) -> "Fragments":
-    """clip_faces (culling only) -> rasterize_meshes -> face indices mapped back to the unclipped mesh."""
-    keep, straddles = clip_cull(vproj, faces)
-    fr = rasterize(vproj, faces[keep], S, blur_radius, K, **kw)
+    """clip_faces -> rasterize_meshes -> convert_clipped_rasterization_to_original_faces: face indices are mapped
+    back to the unclipped mesh and the barycentrics of cut faces are expressed in the unclipped face."""
+    vproj = np.ascontiguousarray(vproj, np.float32)
+    faces = np.ascontiguousarray(faces, np.int32)
+    fv = vproj[faces]
+    if not (fv[:, :, 2] < Z_CLIP).any():       # clip_faces returns its input unchanged
+        return rasterize(vproj, faces, S, blur_radius, K, **kw)
+    cv, idx, nb, conv = clip_faces(fv)
+    fr = rasterize_fv(cv, nb, S, blur_radius, K, **kw)
     p2f = fr.pix_to_face
-    fr.pix_to_face = np.where(p2f >= 0, keep[np.maximum(p2f, 0)].astype(np.int32) if len(keep) else p2f, p2f).astype(np.int32)
-    fr.straddles = straddles
+    hit = p2f >= 0
+    safe = np.maximum(p2f, 0)
+    if len(idx):
+        cut = hit & (idx[safe] >= 0) & ~np.all(conv[safe] == np.eye(3, dtype=np.float32), axis=(-1, -2))
+        nb_ = np.einsum("...k,...kj->...j", fr.bary, conv[safe]).astype(np.float32)
+        fr.bary = np.where(cut[..., None], nb_, fr.bary).astype(np.float32)
+        fr.pix_to_face = np.where(hit, idx[safe], p2f).astype(np.int32)
+    fr.straddles = bool((nb >= 0).any() or len(idx) != len(np.unique(idx)) or
+                        (((fv[:, :, 2] < Z_CLIP).sum(1) % 3) != 0).any())
     return fr
 
 

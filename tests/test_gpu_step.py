@@ -238,8 +238,7 @@ def test_three_object_per_env_meshes(oracle, cuda_lib):
         ref = oracle.OracleOcclusionEnv(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, img_size=S)
         ref.reset(radius=4.0, azimuth=az0[e], elevation=0.1)
         _, rew, done, _ = ref.step(act[e])
-        if st[e] & 1:
-            continue  # z-clip flagged: triangle clipping not implemented, results not comparable
+        assert not (st[e] & 1)
         assert np.array_equal(eng.pix_to_face[e].cpu().numpy(), ref.last.pix_to_face)
         assert np.array_equal(eng.nhits[e].cpu().numpy(), ref.last.nhits)
         np.testing.assert_allclose(eng.alphas[e].cpu().numpy(), ref.last.alphas, rtol=RTOL, atol=ATOL_A)
@@ -340,11 +339,12 @@ def test_dense_meshes_many_overflowing_pixels(oracle, cuda_lib, seed, az, el):
     torch.testing.assert_close(eng.alphas, eng2.alphas, rtol=RTOL, atol=ATOL_A)
 
 
-@pytest.mark.parametrize("variant", ["far_camera", "k10", "no_cull", "norm_object_size", "tiny_image", "near_camera_flag"])
+@pytest.mark.parametrize("variant", ["far_camera", "k10", "no_cull", "norm_object_size", "tiny_image", "near_camera_clip"])
 def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     """Edge cases of the raster configuration: sub-pixel faces (all hits pile up on a few pixels), a small K
     (the nearest-K rule everywhere), no back-face culling (negative-area faces take the reference-order path),
-    the normWithObjectSize reward branch (environment.py:324), a 16x16 image, and the z-clip flag."""
+    the normWithObjectSize reward branch (environment.py:324), a 16x16 image, and a camera inside the occluder's
+    bounding box (faces cut at z_clip = znear/2 by clip_faces; the differentiable step refuses such frames)."""
     from occlusionenv_b200.engine import OcclusionEngine
     sc = default_scene("teapot")
     S, K, cull, radius, norm = 64, 100, True, 4.0, False
@@ -358,19 +358,13 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
         norm = True
     elif variant == "tiny_image":
         S = 16
-    elif variant == "near_camera_flag":
-        radius = 2.3  # closer than znear/2 to the shifted teapot
+    elif variant == "near_camera_clip":
+        radius = 2.3  # closer than znear/2 to the shifted teapot: clip_faces cuts / removes faces
     cfg = RasterConfig(image_size=S, faces_per_pixel=K, cull_backfaces=cull, norm_with_object_size=norm)
     eng = OcclusionEngine(sc, 1, cfg, debug_outputs=True)
     az, el = 1.45, 0.1
     eng.reset(radius=radius, azimuth=az, elevation=el)
     st = int(eng.status[0])
-    if variant == "near_camera_flag":
-        assert st & 1, "a vertex closer than znear/2 must raise the z-clip flag"
-        from occlusionenv_b200 import _lib as L
-        with pytest.raises(L.OcclError):
-            eng.check_status()
-        return
     assert not (st & (1 | 4)), st
     C, R, T = oracle.pose_lookat(radius, el, az)
     vproj = oracle.project(sc.verts, R, T)
@@ -378,10 +372,12 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     for i in range(sc.n_obj):
         v0, v1 = sc.obj_vert_start[i], sc.obj_vert_start[i + 1]
         f0, f1 = sc.obj_face_start[i], sc.obj_face_start[i + 1]
-        fr = oracle.rasterize(vproj[v0:v1], sc.faces[f0:f1] - v0, S, oracle.BLUR_RADIUS, K, cull_backfaces=cull)
+        fr = oracle.rasterize_clipped(vproj[v0:v1], sc.faces[f0:f1] - v0, S, oracle.BLUR_RADIUS, K, cull_backfaces=cull)
         alphas.append(oracle.silhouette(fr))
         nhits.append(fr.nhits)
-    scene = oracle.rasterize(vproj, sc.faces, S, 0.0, 1, cull_backfaces=cull)
+        if variant == "near_camera_clip" and i == 1:
+            assert fr.straddles, "the test pose must cut faces of the occluder"
+    scene = oracle.rasterize_clipped(vproj, sc.faces, S, 0.0, 1, cull_backfaces=cull)
     assert np.array_equal(eng.nhits[0].cpu().numpy(), np.stack(nhits))
     assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), scene.pix_to_face[..., 0])
     assert np.array_equal(eng.obs[0, 3].cpu().numpy(), scene.zbuf[..., 0])
@@ -394,6 +390,14 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     np.testing.assert_allclose(float(eng.object_mass[0]), mass, rtol=RTOL)
     if variant in ("far_camera", "k10"):
         assert (np.stack(nhits) > K).any()
+    if variant == "near_camera_clip":
+        np.testing.assert_allclose(eng.bary[0].cpu().numpy(), scene.bary[..., 0, :], rtol=1e-5, atol=1e-6)
+        # gradients through cut faces are not implemented: the differentiable step flags the frame and the host raises
+        from occlusionenv_b200 import _lib as L
+        eng.step(torch.zeros(1, 2, device="cuda"), with_grad=True)
+        assert int(eng.status[0]) & 1
+        with pytest.raises(L.OcclError):
+            eng.check_status()
 
 
 def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
@@ -441,6 +445,11 @@ def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
     add((1.5, 1.5), (1.7, 1.5), (1.5, 1.8))                           # off screen
     add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 3e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4))  # sub-pixel
     add((c(10) + 1e-4, c(10) + 1e-4), (c(10) + 1e-4, c(10) + 3e-4), (c(10) + 3e-4, c(10) + 1e-4))
+    # one / two vertices nearer than z_clip: cut by clip_faces into two neighbouring triangles / one triangle
+    add((-0.6, -0.6), (0.0, 0.5), (0.6, -0.6), z=(2.0, 0.2, 2.0))
+    add((-0.3, 0.2), (0.1, 0.7), (0.5, 0.1), z=(0.3, 1.5, 0.45))
+    add((0.2, -0.7), (0.5, -0.2), (0.8, -0.8), z=(0.45, 3.0, 3.0))
+    add((-0.8, 0.1), (-0.6, 0.6), (-0.2, 0.2), z=(1.0, 0.49, 0.9))
     # wholly nearer than z_clip = znear/2: removed by clip_faces (they would cover half the image otherwise)
     add((-0.9, -0.9), (0.9, -0.9), (0.0, 0.9), z=(0.3, 0.45, 0.4))
     add((-0.5, -0.5), (0.5, -0.5), (0.0, 0.5), z=(0.2, 0.2, 0.2))
@@ -458,6 +467,7 @@ def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
         Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
         eng.render(Rt, Tt, Ct)
         assert not (int(eng.status[0]) & (1 | 4))
+        assert ref.zclip_straddle
         assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits), exact
         assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), ref.pix_to_face), exact
         assert np.array_equal(eng.obs[0, 3].cpu().numpy(), ref.obs[3]), exact
