@@ -156,3 +156,59 @@ def test_state_machine_golden_trajectory(oracle):
         assert np.float32(env.elevation) == g["elevations"][i] and np.float32(env.azimuth) == g["azimuths"][i]
     # zero action: no move (environment.py:358), reward = -0.2 exactly
     assert g["rewards"][2] == np.float32(-0.2)
+
+
+def test_clip_faces_restatement_invariants(oracle):
+    """oracle.clip_faces (pytorch3d renderer/mesh/clip.py, cases 1-4): cut vertices lie on z = z_clip, the
+    conversion matrices reproduce the cut vertices from the uncut face (in view space), neighbours name each other,
+    and the hard coverage of a cut face equals an independent float64 point-in-polygon test of its front part."""
+    rng = np.random.default_rng(3)
+    s = float(oracle.PROJ_SCALE)
+    zc = float(oracle.Z_CLIP)
+    S = 48
+    for trial in range(12):
+        n_behind = 1 + trial % 2
+        view = np.zeros((3, 3))
+        view[:, :2] = rng.uniform(-1.0, 1.0, (3, 2))
+        z = rng.uniform(1.0, 3.0, 3)
+        z[rng.permutation(3)[:n_behind]] = rng.uniform(0.05, 0.45, n_behind)
+        view[:, 2] = z
+        ndc = np.stack([s * view[:, 0] / view[:, 2], s * view[:, 1] / view[:, 2], view[:, 2]], 1).astype(np.float32)
+        cv, idx, nb, conv = oracle.clip_faces(ndc[None])
+        assert len(cv) == (2 if n_behind == 1 else 1) and (idx == 0).all()
+        if n_behind == 1:
+            assert nb.tolist() == [1, 0]
+        else:
+            assert nb.tolist() == [-1]
+        for t in range(len(cv)):
+            assert (cv[t][:, 2] >= zc - 1e-6).all()
+            back = conv[t].astype(np.float64) @ view                      # view-space positions of the cut vertices
+            np.testing.assert_allclose(back[:, 2], cv[t][:, 2], rtol=2e-5, atol=2e-6)
+            np.testing.assert_allclose(s * back[:, 0] / back[:, 2], cv[t][:, 0], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(s * back[:, 1] / back[:, 2], cv[t][:, 1], rtol=1e-4, atol=1e-5)
+            np.testing.assert_allclose(conv[t].sum(1), 1.0, atol=1e-6)
+        # hard coverage vs float64 polygon test (either winding: no culling)
+        faces = np.array([[0, 1, 2]], np.int32)
+        fr = oracle.rasterize_clipped(ndc, faces, S, 0.0, 1, cull_backfaces=False)
+        got = fr.pix_to_face[..., 0] >= 0
+        poly = []
+        for a in range(3):                                                # Sutherland-Hodgman against z >= zc, in view space
+            p, q = view[a], view[(a + 1) % 3]
+            if p[2] >= zc:
+                poly.append(p)
+            if (p[2] >= zc) != (q[2] >= zc):
+                w = (p[2] - zc) / (p[2] - q[2])
+                poly.append(p + (q - p) * w)
+        poly = np.array(poly)
+        pn = np.stack([s * poly[:, 0] / poly[:, 2], s * poly[:, 1] / poly[:, 2]], 1)
+        c = -1.0 + (2.0 * (S - 1 - np.arange(S)) + 1.0) / S               # pixel centres, index -> NDC (A.3)
+        X, Y = np.meshgrid(c, c)
+        sign = []
+        for a in range(len(pn)):
+            p, q = pn[a], pn[(a + 1) % len(pn)]
+            sign.append((X - p[0]) * (q[1] - p[1]) - (Y - p[1]) * (q[0] - p[0]))
+        sign = np.stack(sign)
+        want = (sign > 0).all(0) | (sign < 0).all(0)
+        near_edge = (np.abs(sign) < 1e-4).any(0)
+        assert ((got == want) | near_edge).all(), trial
+        assert fr.straddles

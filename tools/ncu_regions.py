@@ -23,7 +23,8 @@ marks = [
     ("div_rn_hoisted / sfu", "// raw SFU approximations", "// clipped-barycentric depth"),
     ("soft_accumulate / hard_update", "__device__ __forceinline__ void soft_accumulate", "// One face against the pixels"),
     ("raster_face_pixels", "// One face against the pixels", "// Tangent terms of one soft hit"),
-    ("tile prologue (mask, init)", "raster_kernel(const RasterParams p) {", "// ---- every warp on its own"),
+    ("tile prologue (mask, init)", "__device__ __forceinline__ void raster_tile(", "// ---- every warp on its own"),
+    ("cut faces (z-clip)", "// z-clip: pytorch3d renderer/mesh/clip.py::clip_faces", "// kernel 2: per-env face setup"),
     ("scan + stage", "// ---- every warp on its own", "// process batches of (up to) 32 staged faces"),
     ("batch sort + pass dispatch", "// process batches of (up to) 32 staged faces", "// dense exact-depth pass over this warp"),
     ("deferred depth pass", "// dense exact-depth pass over this warp", "// ---- big faces: the whole CTA"),
