@@ -223,15 +223,13 @@ class OcclusionEngine:
 
     def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP) -> int:
         """Host-syncing check of the per-env status words; raises on conditions the kernels flag
-        instead of computing (z-clip needed, selection buffers exceeded)."""
-        st = self.status if self.n == 1 else self.status.max().reshape(1)  # OR of single-bit flags ~ max is enough to test
-        if self.n > 1:
-            # bitwise OR over envs
-            st = torch.bitwise_or(torch.bitwise_and(self.status, 1).max(), torch.bitwise_or(
-                torch.bitwise_and(self.status, 2).max(), torch.bitwise_or(
-                    torch.bitwise_and(self.status, 4).max(), torch.bitwise_and(self.status, 8).max()))).reshape(1)
-        val = int(st.item())
+        instead of computing (gradient through faces cut at z_clip, selection buffers exceeded)."""
+        # bitwise OR over the envs: every flag is a single bit, so the max of each masked word will do
+        bits = (L.ST_ZCLIP, L.ST_KOVERFLOW, L.ST_HITCAP, L.ST_OVFCAP, L.ST_CLIPPED)
+        masked = torch.stack([torch.bitwise_and(self.status, b).max() for b in bits])  # one device->host copy
+        val = sum(int(v) for v in masked.tolist())
         if val & raise_on:
-            raise L.OcclError(f"env status flags set: {val & raise_on:#x} (1=z-clip needed: a vertex is closer than "
-                              "znear/2 and pytorch3d would clip triangles, 4=more than 2560 hits on one pixel)")
+            raise L.OcclError(f"env status flags set: {val & raise_on:#x} (1 = the differentiable step met a face cut at z_clip = "
+                              "znear/2: no gradient flows through cut faces, 4 = more candidate faces on one pixel than the "
+                              "top-K selection buffer holds)")
         return val
