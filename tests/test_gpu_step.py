@@ -69,6 +69,25 @@ def test_golden_fixtures(cuda_lib, occ):
         np.testing.assert_allclose(float(eng.loss[k]), float(g[f"loss{k}"]), rtol=RTOL, atol=1e-6)
 
 
+def test_golden_fixture_near_camera_cut_faces(cuda_lib):
+    """tests/golden/scene_teapot_near_64.npz: 142 faces cut at z_clip (clip_faces cases 3/4), 1590 removed."""
+    g = np.load(os.path.join(GOLD, "scene_teapot_near_64.npz"))
+    sc = default_scene("teapot")
+    eng = _engine(sc, 1, 64, debug_outputs=True)
+    R, T, C = (torch.tensor(g[k][None], device="cuda").contiguous() for k in ("R", "T", "C"))
+    eng.render(R, T, C)
+    assert eng.check_status() & 16, "the clip-capable kernel must have taken this env"
+    assert np.array_equal(eng.pix_to_face[0].cpu().numpy().astype(np.int16), g["pix_to_face"])
+    assert np.array_equal(eng.obs[0, 3].cpu().numpy(), g["zbuf"])
+    assert np.array_equal(eng.nhits[0].cpu().numpy().astype(np.int16), g["nhits"])
+    assert np.array_equal(eng.n_covered[0].cpu().numpy(), g["n_covered"])
+    assert np.array_equal(eng.n_visible[0].cpu().numpy(), g["n_visible"])
+    np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), g["alphas"], rtol=RTOL, atol=ATOL_A)
+    np.testing.assert_allclose(eng.obs[0, 0].cpu().numpy(), g["rgb"], rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(eng.bary[0].cpu().numpy(), g["bary"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(float(eng.loss[0]), float(g["loss"]), rtol=RTOL, atol=1e-6)
+
+
 def test_trajectory_matches_oracle_state_machine(oracle, cuda_lib):
     """reset + several steps for a batch of envs: reward / done / loss / state, every step."""
     sc = default_scene("teapot")
@@ -475,3 +494,24 @@ def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
         assert np.array_equal(eng.n_visible[0].cpu().numpy(), ref.n_visible)
         np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
         np.testing.assert_allclose(eng.obs[0, :3].cpu().numpy(), ref.obs[:3], rtol=RTOL, atol=1e-6)
+
+
+def test_dataset_generator_writes_reference_layout(cuda_lib, tmp_path):
+    """datasetGenerator.py:68-124 batched: run folders, 3 images per frame, params rows with finite gradients."""
+    import pickle
+
+    import cv2
+
+    from occlusionenv_b200.datasetGenerator import generate_dataset
+    n = generate_dataset(str(tmp_path / "Dataset"), num_obj=3, num_frame=4, img_size=64, batch=2, azimuth=1.5, seed=1)
+    assert n == 12
+    for i in range(3):
+        run = tmp_path / "Dataset" / f"run_{i}"
+        params = pickle.load(open(run / "params.pickle", "rb")).reshape(-1, 5)
+        assert params.shape == (4, 5) and np.array_equal(params[:, 0], np.arange(4)) and np.isfinite(params).all()
+        assert (np.abs(params[:, 2] - 1.5) < 0.3).all()
+        for j in range(4):
+            assert cv2.imread(str(run / "RGB" / f"{j}.jpg")).shape == (64, 64, 3)
+            occl = cv2.imread(str(run / "Occl" / f"{j}.png"), cv2.IMREAD_UNCHANGED)
+            depth = cv2.imread(str(run / "Depth" / f"{j}.png"), cv2.IMREAD_UNCHANGED)
+            assert occl.shape == (64, 64) and depth.shape == (64, 64) and depth.max() > 40

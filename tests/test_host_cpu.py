@@ -169,3 +169,37 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libocclusion_oracle" not in txt, fn
+
+
+def test_dataset_generator_file_formats(tmp_path):
+    """datasetGenerator.py:99-124: RGB jpg = img_as_ubyte(obs[..., :3]), Occl png = img_as_ubyte(alpha), Depth png =
+    depth with background -1 -> 0, times 51, truncated; params.pickle = flat float64 rows [j, el, az, g0, g1]."""
+    import pickle
+
+    import cv2
+
+    from occlusionenv_b200 import datasetGenerator as G
+    S = 16
+    rng = np.random.default_rng(0)
+    obs = rng.uniform(0, 1, (4, S, S)).astype(np.float32)
+    obs[3] = rng.uniform(2.0, 4.9, (S, S)).astype(np.float32)
+    obs[3, :4] = -1.0
+    obs[0, 0, 0] = 1.0000001  # shaded colour one ulp above 1: skimage would raise, this clips
+    occl = rng.uniform(0, 1, (S, S)).astype(np.float32)
+    assert G.img_as_ubyte(np.array([0.0, 0.5, 1.0, -0.2])).tolist() == [0, 128, 255, 0]
+    d = G.encode_depth(obs)
+    assert (d[:4] == 0).all() and d[5, 5] == int(np.float32(obs[3, 5, 5] * np.float32(51)))
+    run = tmp_path / "run_0"
+    for sub in ("Depth", "RGB", "Occl"):
+        os.makedirs(run / sub)
+    G.write_frame(str(run), 3, obs, occl)
+    png = cv2.imread(str(run / "Occl" / "3.png"), cv2.IMREAD_UNCHANGED)
+    assert png.shape == (S, S) and np.array_equal(png, G.encode_occlusion(occl))
+    dep = cv2.imread(str(run / "Depth" / "3.png"), cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(dep, d)
+    jpg = cv2.imread(str(run / "RGB" / "3.jpg"), cv2.IMREAD_UNCHANGED)
+    assert jpg.shape == (S, S, 3)
+    rows = np.arange(10, dtype=np.float64).reshape(2, 5)
+    G.write_params(str(run), rows)
+    back = pickle.load(open(run / "params.pickle", "rb"))
+    assert back.shape == (10,) and back.dtype == np.float64 and np.array_equal(back, rows.reshape(-1))

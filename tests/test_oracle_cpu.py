@@ -212,3 +212,16 @@ def test_clip_faces_restatement_invariants(oracle):
         near_edge = (np.abs(sign) < 1e-4).any(0)
         assert ((got == want) | near_edge).all(), trial
         assert fr.straddles
+
+
+def test_oracle_reproduces_near_camera_golden(oracle):
+    """Camera inside the occluder's bounding box: 70 + 72 faces of the scene are cut at z_clip, 1590 removed."""
+    g = np.load(os.path.join(GOLD, "scene_teapot_near_64.npz"))
+    sc = default_scene("teapot")
+    r = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 64, g["C"], g["R"], g["T"])
+    assert r.zclip_straddle
+    assert np.array_equal(r.pix_to_face.astype(np.int16), g["pix_to_face"])
+    assert np.array_equal(r.zbuf, g["zbuf"]) and np.array_equal(r.alphas, g["alphas"])
+    assert np.array_equal(r.nhits.astype(np.int16), g["nhits"])
+    assert np.array_equal(r.n_covered, g["n_covered"]) and np.array_equal(r.n_visible, g["n_visible"])
+    assert np.float32(r.loss) == g["loss"]
