@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 METRIC = "env-steps/sec (render+reward, fwd)"
 UNIT = "env-steps/s"
 
@@ -115,7 +116,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -186,7 +187,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("OCCL_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        if "OCCL_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["OCCL_NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device(dev))
     from occlusionenv_b200.SubProcVecEnv import BatchedOcclusionVecEnv
     from occlusionenv_b200.config import RasterConfig
@@ -373,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
     }
     if gather is not None:
         line["gather"] = gather
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -397,6 +399,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints "NCCL version ..." on fd 1) and any stray
+    # print are sent to stderr, the JSON line goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
