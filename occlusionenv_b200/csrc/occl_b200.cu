@@ -1,17 +1,21 @@
 // occl_b200.cu -- hand-written sm_100a kernels + the C-ABI of include/occl_b200.h.
 //
 // Hot path of MILAB-IIT-CV/OcclusionEnv (environment.py:352-396 step, :302-328 reset render) for N
-// environments at once.  Four kernels per transition, all on the caller's stream:
+// environments at once.  Six launches per transition, all on the caller's stream:
 //
-//   pose_kernel      one thread per env: action -> (el, az) -> camera centre -> look-at R, T, with
-//                    forward-mode tangents d/d_el, d/d_az carried as dual numbers       (north-star 1)
-//   project_kernel   one thread per (env, vertex): world -> view -> NDC, z := view z    (north-star 1)
-//   raster_kernel    one CTA per (env, image tile): faces are set up, culled and compacted into a
-//                    shared-memory list with warp ballots (2); a warp per face scatters soft-
-//                    silhouette factors and the nearest-z key into per-pixel accumulators in shared
-//                    memory (3,4); the epilogue blends, shades, writes RGBD / occlusion map with
-//                    coalesced stores and reduces loss, gradient and pixel counts with warp shuffles (5,6)
-//   finalize_kernel  one thread per env: tile partials -> loss, reward, done, state, d reward/d action
+//   pose_kernel        one thread per env: action -> (el, az) -> camera centre -> look-at R, T, with
+//                      forward-mode tangents d/d_el, d/d_az carried as dual numbers       (north-star 1)
+//   project_kernel     one thread per (env, vertex): world -> view -> NDC, z := view z    (north-star 1)
+//   face_setup_kernel  one CTA per env: culls (back face, degenerate, z, z_clip), exact pixel ranges, per-face
+//                      lighting, warp-ballot compaction of the live faces, mask of non-empty tiles  (2)
+//   raster_kernel      one CTA per (env, image tile): warps stage the faces of the tile in shared memory and
+//                      scatter soft-silhouette factors and the nearest-z key into per-pixel accumulators in
+//                      shared memory (3,4); pixels with more than K hits get the nearest-K rule; the epilogue
+//                      blends, shades, writes RGBD / occlusion map with coalesced stores and reduces loss,
+//                      gradient and pixel counts with warp shuffles (5,6)
+//   raster_clip_kernel one CTA per env, only for envs with faces cut at z_clip (clip_faces): the same tile
+//                      rasteriser in its clip-capable instantiation
+//   finalize_kernel    one thread per env: tile partials -> loss, reward, done, state, d reward/d action
 //
 // Bit-exactness: every expression that decides a hit, its sign, the nearest face or the K-nearest
 // set is evaluated in the operation order of pytorch3d's rasteriser with
