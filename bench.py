@@ -157,7 +157,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def stop(self):
         self._stop_evt.set()
@@ -177,8 +177,8 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload on ONE host core (scalar port): ~10-15 s
-        n_env = 24 if args.size <= 128 else 6
+        # bounded sample of the same workload on ONE host core (scalar port): ~12-25 s
+        n_env = 96 if args.size <= 128 else 24
         v, ms = cpu_reference_run(args.occluder, args.size, 1, n_env, 1, 0)
         cpu_base = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                     "sample": f"{n_env} env-steps of the same workload, sequential SimpleVecEnv loop on 1 core "
