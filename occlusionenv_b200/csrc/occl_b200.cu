@@ -37,6 +37,13 @@
 #ifndef OCCL_TILE_H
 #define OCCL_TILE_H 32
 #endif
+#ifndef OCCL_TILE2_W
+#define OCCL_TILE2_W 32        // second compile-time tile: half the pixels, for scenes with 3-4 objects or dense meshes
+#endif                         // (smaller accumulators -> 4 CTAs/SM instead of 3, more tiles to balance: config 3 +37 %,
+#ifndef OCCL_TILE2_H           //  config 2 -14 %)
+#define OCCL_TILE2_H 16
+#endif
+#define OCCL_DENSE_FACES 16384 // default tile = the second one from this many faces (or 3 objects) on
 #define OCCL_WARPS (OCCL_THREADS / 32)
 #ifndef SETUP_THREADS
 #define SETUP_THREADS 256     // face_setup_kernel: one CTA per env (1024 measured slower: 1 CTA per SM)
@@ -2198,8 +2205,10 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->tile_w == 0 || c->tile_h == 0) {
     const int S = c->image_size;
     // square tiles split the fewest faces; 32x32 px (1024 px of accumulators) keeps 3 CTAs per SM
-    c->tile_w = S < OCCL_TILE_W ? S : OCCL_TILE_W;
-    c->tile_h = S < OCCL_TILE_H ? S : OCCL_TILE_H;
+    const bool dense = c->n_obj >= 3 || c->n_faces >= OCCL_DENSE_FACES;
+    const int tw = dense ? OCCL_TILE2_W : OCCL_TILE_W, th = dense ? OCCL_TILE2_H : OCCL_TILE_H;
+    c->tile_w = S < tw ? S : tw;
+    c->tile_h = S < th ? S : th;
   }
   if (c->tile_w < 1 || c->tile_h < 1 || c->tile_w > 256 || c->tile_h > 256) return OCCL_E_INVALID;
   if (tile_smem_bytes(c, with_grad) + 8 * 1024 > 227 * 1024) return OCCL_E_SMEM;
@@ -2357,21 +2366,23 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     CK(cudaGetLastError(), "face_setup_kernel");
   }
   const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
+  const bool fixed2 = !fixed && c.tile_w == OCCL_TILE2_W && c.tile_h == OCCL_TILE2_H;
 #define OCCL_LAUNCH_RASTER(G, W, H, D)                                                                                   \
   do {                                                                                                                   \
     CK(cudaFuncSetAttribute(raster_kernel<G, W, H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
     raster_kernel<G, W, H, D><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
   } while (0)
+#define OCCL_LAUNCH_RASTER_G(G)                                                                 \
+  do {                                                                                          \
+    if (fixed && !dbg) OCCL_LAUNCH_RASTER(G, OCCL_TILE_W, OCCL_TILE_H, false);                  \
+    else if (fixed) OCCL_LAUNCH_RASTER(G, OCCL_TILE_W, OCCL_TILE_H, true);                      \
+    else if (fixed2 && !dbg) OCCL_LAUNCH_RASTER(G, OCCL_TILE2_W, OCCL_TILE2_H, false);          \
+    else if (fixed2) OCCL_LAUNCH_RASTER(G, OCCL_TILE2_W, OCCL_TILE2_H, true);                   \
+    else OCCL_LAUNCH_RASTER(G, 0, 0, true);                                                     \
+  } while (0)
   const bool dbg = out.alphas || out.pix_to_face || out.bary || out.nhits;
-  if (grad) {
-    if (fixed && !dbg) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H, false);
-    else if (fixed) OCCL_LAUNCH_RASTER(true, OCCL_TILE_W, OCCL_TILE_H, true);
-    else OCCL_LAUNCH_RASTER(true, 0, 0, true);
-  } else {
-    if (fixed && !dbg) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, false);
-    else if (fixed) OCCL_LAUNCH_RASTER(false, OCCL_TILE_W, OCCL_TILE_H, true);
-    else OCCL_LAUNCH_RASTER(false, 0, 0, true);
-  }
+  if (grad) OCCL_LAUNCH_RASTER_G(true); else OCCL_LAUNCH_RASTER_G(false);
+#undef OCCL_LAUNCH_RASTER_G
   // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile
   if (grad) {
     CK(cudaFuncSetAttribute(raster_clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
