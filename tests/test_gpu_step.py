@@ -272,7 +272,7 @@ def test_tile_shapes_and_odd_image_size(oracle, cuda_lib):
     _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.1, 1.4, 4.0)
     ref = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
     Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
-    for tw, th in [(0, 0), (16, 16), (50, 8), (64, 32), (43, 43), (7, 5)]:
+    for tw, th in [(0, 0), (32, 16), (16, 16), (50, 8), (64, 32), (43, 43), (7, 5)]:  # (0,0) and (32,16): the compile-time tiles
         eng = OcclusionEngine(sc, 1, RasterConfig(image_size=S, tile_w=tw, tile_h=th), debug_outputs=True)
         eng.render(Rt, Tt, Ct)
         eng.check_status()
