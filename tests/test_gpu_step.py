@@ -70,7 +70,8 @@ def test_golden_fixtures(cuda_lib, occ):
 
 
 def test_golden_fixture_near_camera_cut_faces(cuda_lib):
-    """tests/golden/scene_teapot_near_64.npz: 142 faces cut at z_clip (clip_faces cases 3/4), 1590 removed."""
+    """tests/golden/scene_teapot_near_64.npz: camera inside the target's bounding box -- faces cut at z_clip
+    (clip_faces cases 3/4) are visible on a few hundred pixels, faces nearer than z_clip are removed."""
     g = np.load(os.path.join(GOLD, "scene_teapot_near_64.npz"))
     sc = default_scene("teapot")
     eng = _engine(sc, 1, 64, debug_outputs=True)
@@ -358,7 +359,7 @@ def test_dense_meshes_many_overflowing_pixels(oracle, cuda_lib, seed, az, el):
     torch.testing.assert_close(eng.alphas, eng2.alphas, rtol=RTOL, atol=ATOL_A)
 
 
-@pytest.mark.parametrize("variant", ["far_camera", "k10", "no_cull", "norm_object_size", "tiny_image", "near_camera_clip"])
+@pytest.mark.parametrize("variant", ["far_camera", "k10", "no_cull", "norm_object_size", "tiny_image", "near_camera_clip", "near_camera_clip_k3"])
 def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     """Edge cases of the raster configuration: sub-pixel faces (all hits pile up on a few pixels), a small K
     (the nearest-K rule everywhere), no back-face culling (negative-area faces take the reference-order path),
@@ -377,11 +378,13 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
         norm = True
     elif variant == "tiny_image":
         S = 16
-    elif variant == "near_camera_clip":
-        radius = 2.3  # closer than znear/2 to the shifted teapot: clip_faces cuts / removes faces
+    elif variant.startswith("near_camera_clip"):
+        radius = 1.0  # camera inside the target teapot's bounding box: clip_faces removes faces and cuts visible ones
+        if variant.endswith("k3"):
+            K = 3     # ... and the nearest-K rule has to pick among hits on cut faces
     cfg = RasterConfig(image_size=S, faces_per_pixel=K, cull_backfaces=cull, norm_with_object_size=norm)
     eng = OcclusionEngine(sc, 1, cfg, debug_outputs=True)
-    az, el = 1.45, 0.1
+    az, el = (1.0, 0.1) if variant.startswith("near_camera_clip") else (1.45, 0.1)
     eng.reset(radius=radius, azimuth=az, elevation=el)
     st = int(eng.status[0])
     assert not (st & (1 | 4)), st
@@ -394,8 +397,14 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
         fr = oracle.rasterize_clipped(vproj[v0:v1], sc.faces[f0:f1] - v0, S, oracle.BLUR_RADIUS, K, cull_backfaces=cull)
         alphas.append(oracle.silhouette(fr))
         nhits.append(fr.nhits)
-        if variant == "near_camera_clip" and i == 1:
-            assert fr.straddles, "the test pose must cut faces of the occluder"
+        if variant.startswith("near_camera_clip") and i == 0:
+            assert fr.straddles, "the test pose must cut faces of the target"
+            zf = vproj[v0:v1][sc.faces[f0:f1] - v0][:, :, 2]
+            cut = np.nonzero(((zf < 0.5).sum(1) % 3) != 0)[0]
+            seen = np.isin(fr.pix_to_face, cut) & (fr.pix_to_face >= 0)
+            assert seen.any(-1).sum() > 100, "cut faces must be visible"
+            if K == 3:
+                assert (seen.any(-1) & (fr.nhits > K)).sum() > 10, "cut faces must take part in the nearest-K rule"
     scene = oracle.rasterize_clipped(vproj, sc.faces, S, 0.0, 1, cull_backfaces=cull)
     assert np.array_equal(eng.nhits[0].cpu().numpy(), np.stack(nhits))
     assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), scene.pix_to_face[..., 0])
@@ -407,9 +416,9 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
     objsq = float(np.sum((alphas[0] + alphas[1]).astype(np.float64) ** 2))
     mass = (objsq if norm else loss) + 1.0
     np.testing.assert_allclose(float(eng.object_mass[0]), mass, rtol=RTOL)
-    if variant in ("far_camera", "k10"):
+    if variant in ("far_camera", "k10", "near_camera_clip_k3"):
         assert (np.stack(nhits) > K).any()
-    if variant == "near_camera_clip":
+    if variant.startswith("near_camera_clip"):
         np.testing.assert_allclose(eng.bary[0].cpu().numpy(), scene.bary[..., 0, :], rtol=1e-5, atol=1e-6)
         # gradients through cut faces are not implemented: the differentiable step flags the frame and the host raises
         from occlusionenv_b200 import _lib as L

@@ -215,7 +215,7 @@ def test_clip_faces_restatement_invariants(oracle):
 
 
 def test_oracle_reproduces_near_camera_golden(oracle):
-    """Camera inside the occluder's bounding box: 70 + 72 faces of the scene are cut at z_clip, 1590 removed."""
+    """Camera inside the target's bounding box: visible faces cut at z_clip, faces nearer than z_clip removed."""
     g = np.load(os.path.join(GOLD, "scene_teapot_near_64.npz"))
     sc = default_scene("teapot")
     r = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 64, g["C"], g["R"], g["T"])

@@ -65,13 +65,13 @@ traj.update(rewards=np.asarray(rews, np.float32), dones=np.asarray(dones), losse
 np.savez_compressed(os.path.join(out_dir, "trajectory_teapot_64.npz"), **traj)
 print("trajectory", traj["rewards"], traj["dones"], traj["losses"])
 
-# camera inside the occluder's bounding box: clip_faces removes / cuts faces at z_clip = znear/2
+# camera inside the target's bounding box: clip_faces removes faces and cuts visible ones at z_clip = znear/2
 sc = default_scene("teapot")
 S2 = 64
-C, R, T = O.pose_lookat(2.3, 0.1, 1.45)
+C, R, T = O.pose_lookat(1.0, 0.1, 1.0)
 r = O.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S2, C, R, T)
 assert r.zclip_straddle
-np.savez_compressed(os.path.join(out_dir, "scene_teapot_near_64.npz"), C=C, R=R, T=T, pose=np.asarray([2.3, 0.1, 1.45], np.float32),
+np.savez_compressed(os.path.join(out_dir, "scene_teapot_near_64.npz"), C=C, R=R, T=T, pose=np.asarray([1.0, 0.1, 1.0], np.float32),
                     pix_to_face=r.pix_to_face.astype(np.int16), zbuf=r.zbuf, alphas=r.alphas, rgb=r.obs[0],
                     bary=r.bary.astype(np.float32), loss=np.float32(r.loss), nhits=r.nhits.astype(np.int16),
                     n_covered=r.n_covered.astype(np.int32), n_visible=r.n_visible.astype(np.int32))
