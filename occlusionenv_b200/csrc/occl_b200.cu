@@ -297,6 +297,7 @@ struct RasterParams {
   const float2* shade;        // [N][F]
   int* tile_idx;              // [N][n_tiles][tidx_cap] live-list indices of the faces that touch a tile
   int tidx_cap;
+  const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
   // outputs
   float* obs;
   float* occl;
@@ -707,6 +708,9 @@ struct SetupParams {
   uint4* rng;
   int* n_live;
   uint32_t* tile_mask;  // [N][TILE_MASK_WORDS] bit t set: some live face's blur box overlaps tile t
+  int* tile_idx;        // [N][n_tiles][tidx_cap] binning: live-list indices of the faces whose blur box overlaps a tile
+  int* tile_cnt;        // [N][n_tiles] their number (may exceed tidx_cap: the raster kernel then scans the whole live list)
+  int tidx_cap;
   float2* shade;        // [N][F] (ambient + diffuse, specular) of the live faces
   const float* verts;
   long long verts_stride;
@@ -715,16 +719,22 @@ struct SetupParams {
   const uint8_t* env_mask;
 };
 
+// BIN: also bin the live faces per tile (dense scenes; a separate instantiation so that the kernel of config 2 is
+// not touched: its register allocation is as sensitive as the raster kernel's)
+template <bool BIN>
 __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
   __shared__ int s_base;
   __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
+  __shared__ int s_tcnt[BIN ? 32 * TILE_MASK_WORDS : 1];  // faces binned per tile (images of up to 256 tiles)
   const int env = blockIdx.x;
   if (p.env_mask && !p.env_mask[env]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.S;
   for (int i = tid; i < S; i += SETUP_THREADS) tab[i] = pix_to_ndc(S - 1 - i, S);
+  if (BIN)
+    for (int i = tid; i < 32 * TILE_MASK_WORDS; i += SETUP_THREADS) s_tcnt[i] = 0;
   if (tid < TILE_MASK_WORDS) s_tmask[tid] = 0u;
   if (tid == 0) s_base = 0;
   __syncthreads();
@@ -806,6 +816,11 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
           for (int tx = tx_lo; tx <= tx_hi; ++tx) {
             const int t = ty * p.tiles_x + tx;
             atomicOr(&s_tmask[t >> 5], 1u << (t & 31));
+            // binning: the raster CTA of tile t reads this list instead of range-testing every live face
+            if (BIN) {
+              const int pos = atomicAdd(&s_tcnt[t], 1);
+              if (pos < p.tidx_cap) p.tile_idx[((size_t)env * p.n_tiles + t) * p.tidx_cap + pos] = slot;
+            }
           }
       }
       q3 = make_uint4(__float_as_uint(1.0f / l01), __float_as_uint(1.0f / l02), __float_as_uint(1.0f / l12), 0u);
@@ -825,6 +840,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
   __syncthreads();
   if (tid == 0) p.n_live[env] = s_base;
   if (tid < TILE_MASK_WORDS) p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = s_tmask[tid];
+  if (BIN)
+    for (int t = tid; t < p.n_tiles; t += SETUP_THREADS) p.tile_cnt[(size_t)env * p.n_tiles + t] = s_tcnt[t];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1710,7 +1727,16 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  if (tid == 0) { s_chunk = 0; s_big_n = 0; s_tidx_n = 0; }
+  // faces of this tile as binned by the setup kernel (else: every live face of the env is range-tested here)
+  // (compiled only into the dense-scene tile and the generic kernel: the 32x32 kernel of config 2 lost 3 % to the
+  //  mere presence of this branch in its scan loop)
+  constexpr bool BIN = !(TW == OCCL_TILE_W && TH == OCCL_TILE_H);
+  const int n_bin = BIN && p.tile_cnt ? __ldg(p.tile_cnt + (size_t)env * n_tiles + tile) : -1;
+  // (only for well-filled tiles: a chunk of the binned list is 32 faces of THIS tile, and with fewer than four chunks
+  //  per warp the dynamic balancing gets too coarse -- config 2 lost 3.5 % -- while a chunk of the whole live list
+  //  carries only a few faces of the tile)
+  const bool binned = BIN && n_bin >= 128 * OCCL_WARPS && n_bin <= p.tidx_cap;
+  if (tid == 0) { s_chunk = 0; s_big_n = 0; s_tidx_n = binned ? n_bin : 0; }
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
@@ -1733,31 +1759,36 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     // order is spatially coherent, so a strided chunk samples the whole mesh and every chunk carries about
     // the same share of this tile's faces; a pair = 32 B of ranges = one sector).  Warps grab chunks
     // dynamically.
-    const int n_chunks = (n_live + 31) >> 5;
+    const int n_src = binned ? n_bin : n_live;
+    const int n_chunks = (n_src + 31) >> 5;
     for (;;) {
       int c = 0;
       if (lane == 0) c = atomicAdd(&s_chunk, 1);
       c = __shfl_sync(0xffffffffu, c, 0);
       const bool scanning = c < n_chunks;
       if (scanning) {
-        const int k = 2 * (c + n_chunks * (lane >> 1)) + (lane & 1);
+        int k = 2 * (c + n_chunks * (lane >> 1)) + (lane & 1);  // position in the source list
+        const bool valid = k < n_src;
+        if (binned && valid) k = tidx[k];
         bool keep = false;
         int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
         uint4 rg = make_uint4(0, 0, 0, 0);
-        if (k < n_live) {
+        if (valid) {
           rg = __ldg(rng + k);
           cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
           cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
           keep = cx0 <= cx1 && cy0 <= cy1;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        // remember which live faces touch this tile: the K-overflow passes rescan only those
-        int tbase = 0;
-        if (lane == 0 && bal) tbase = atomicAdd(&s_tidx_n, __popc(bal));
-        tbase = __shfl_sync(0xffffffffu, tbase, 0);
-        if (keep) {
+        // without binning: remember which live faces touch this tile (the K-overflow passes rescan only those)
+        if (!binned) {
+          int tbase = 0;
+          if (lane == 0 && bal) tbase = atomicAdd(&s_tidx_n, __popc(bal));
+          tbase = __shfl_sync(0xffffffffu, tbase, 0);
           const int tpos = tbase + __popc(bal & ((1u << lane) - 1u));
-          if (tpos < p.tidx_cap) tidx[tpos] = k;
+          if (keep && tpos < p.tidx_cap) tidx[tpos] = k;
+        }
+        if (keep) {
           const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
           const uint4* __restrict__ src = geo + (size_t)k * 4;
           uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
@@ -2144,7 +2175,7 @@ static int cuda_fail(cudaError_t e, const char* where) {
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, total;
   int tidx_cap;
   int n_tiles;
 };
@@ -2232,6 +2263,7 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->shade = off;    off = align_up(off + sizeof(float2) * (size_t)n * c->n_faces, 256);
   L->tidx_cap = c->n_faces < 8192 ? c->n_faces : 8192;
   L->tile_idx = off; off = align_up(off + sizeof(int) * (size_t)n * L->n_tiles * L->tidx_cap, 256);
+  L->tile_cnt = off; off = align_up(off + sizeof(int) * (size_t)n * L->n_tiles, 256);
   L->total = off;
   return 0;
 }
@@ -2336,6 +2368,9 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.tile_mask = (const uint32_t*)(base + L.tile_mask);
   p.shade = (const float2*)(base + L.shade);
   p.tile_idx = (int*)(base + L.tile_idx); p.tidx_cap = L.tidx_cap;
+  // binning pays for dense scenes only (config 3 +8 %; on config 2 the extra work of the setup kernel costs 3 %)
+  const bool bin = L.n_tiles <= 32 * TILE_MASK_WORDS && (c.n_obj >= 3 || c.n_faces >= OCCL_DENSE_FACES);
+  p.tile_cnt = bin ? (const int*)(base + L.tile_cnt) : nullptr;
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
   p.vtan = grad ? (const float4*)(base + L.vtan) : nullptr;
@@ -2355,6 +2390,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
     sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
     sp.tile_mask = (uint32_t*)(base + L.tile_mask);
+    sp.tile_idx = p.tile_idx; sp.tile_cnt = bin ? (int*)(base + L.tile_cnt) : nullptr; sp.tidx_cap = L.tidx_cap;
     sp.shade = (float2*)(base + L.shade);
     sp.verts = sc.verts; sp.verts_stride = sc.verts_env_stride; sp.cam = p.cam;
     sp.light[0] = c.light[0]; sp.light[1] = c.light[1]; sp.light[2] = c.light[2];
@@ -2362,7 +2398,8 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
     sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
     sp.inv_tile_w = 1.0f / (float)c.tile_w; sp.inv_tile_h = 1.0f / (float)c.tile_h;
-    face_setup_kernel<<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    if (bin) face_setup_kernel<true><<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    else face_setup_kernel<false><<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
   }
   const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
