@@ -49,7 +49,7 @@
 #define SETUP_THREADS 256     // face_setup_kernel: one CTA per env (1024 measured slower: 1 CTA per SM)
 #endif
 #define SETUP_WARPS (SETUP_THREADS / 32)
-#define WBUF_RECS 48          // face records staged per warp (up to 15 pending + 32 new)
+#define WBUF_RECS 48          // face records staged per warp (up to BATCH_MIN - 1 pending + 32 new; the K-overflow hit buffer aliases it)
 #ifndef OCCL_CTAS_FWD
 #define OCCL_CTAS_FWD 4       // resident CTAs per SM the forward kernel is compiled for (64 registers)
 #endif
