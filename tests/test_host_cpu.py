@@ -203,3 +203,12 @@ def test_dataset_generator_file_formats(tmp_path):
     G.write_params(str(run), rows)
     back = pickle.load(open(run / "params.pickle", "rb"))
     assert back.shape == (10,) and back.dtype == np.float64 and np.array_equal(back, rows.reshape(-1))
+
+
+def test_status_bits_match_header():
+    """The Python binding's status bits are the header's (include/occl_b200.h)."""
+    from occlusionenv_b200 import _lib as L
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "occl_b200.h")).read()
+    bits = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define OCCL_ST_(\w+) (\d+)u", hdr)}
+    assert bits == {"ZCLIP": L.ST_ZCLIP, "KOVERFLOW": L.ST_KOVERFLOW, "HITCAP": L.ST_HITCAP, "OVFCAP": L.ST_OVFCAP,
+                    "CLIPPED": L.ST_CLIPPED}
