@@ -43,7 +43,13 @@
 #ifndef OCCL_TILE2_H           //  config 2 -14 %)
 #define OCCL_TILE2_H 16
 #endif
-#define OCCL_DENSE_FACES 16384 // default tile = the second one from this many faces (or 3 objects) on
+#ifndef OCCL_TILE3_W
+#define OCCL_TILE3_W 128       // third compile-time tile: dense meshes (>= OCCL_DENSE_FACES faces): wide and flat
+#endif                         // (config 3: 128x4 13.1 k, 64x8 12.6 k, 32x16 11.8 k env-steps/s; four teapots: 303 k / 318 k / 333 k)
+#ifndef OCCL_TILE3_H
+#define OCCL_TILE3_H 4
+#endif
+#define OCCL_DENSE_FACES 16384 // default tile: the third one from this many faces on, the second one for 3-4 objects
 #define OCCL_WARPS (OCCL_THREADS / 32)
 #ifndef SETUP_THREADS
 #define SETUP_THREADS 256     // face_setup_kernel: one CTA per env (1024 measured slower: 1 CTA per SM)
@@ -2236,8 +2242,9 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->tile_w == 0 || c->tile_h == 0) {
     const int S = c->image_size;
     // square tiles split the fewest faces; 32x32 px (1024 px of accumulators) keeps 3 CTAs per SM
-    const bool dense = c->n_obj >= 3 || c->n_faces >= OCCL_DENSE_FACES;
-    const int tw = dense ? OCCL_TILE2_W : OCCL_TILE_W, th = dense ? OCCL_TILE2_H : OCCL_TILE_H;
+    const bool dense = c->n_faces >= OCCL_DENSE_FACES, many = c->n_obj >= 3;
+    const int tw = dense ? OCCL_TILE3_W : (many ? OCCL_TILE2_W : OCCL_TILE_W);
+    const int th = dense ? OCCL_TILE3_H : (many ? OCCL_TILE2_H : OCCL_TILE_H);
     c->tile_w = S < tw ? S : tw;
     c->tile_h = S < th ? S : th;
   }
@@ -2404,6 +2411,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   }
   const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
   const bool fixed2 = !fixed && c.tile_w == OCCL_TILE2_W && c.tile_h == OCCL_TILE2_H;
+  const bool fixed3 = !fixed && !fixed2 && c.tile_w == OCCL_TILE3_W && c.tile_h == OCCL_TILE3_H;
 #define OCCL_LAUNCH_RASTER(G, W, H, D)                                                                                   \
   do {                                                                                                                   \
     CK(cudaFuncSetAttribute(raster_kernel<G, W, H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
@@ -2415,6 +2423,8 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     else if (fixed) OCCL_LAUNCH_RASTER(G, OCCL_TILE_W, OCCL_TILE_H, true);                      \
     else if (fixed2 && !dbg) OCCL_LAUNCH_RASTER(G, OCCL_TILE2_W, OCCL_TILE2_H, false);          \
     else if (fixed2) OCCL_LAUNCH_RASTER(G, OCCL_TILE2_W, OCCL_TILE2_H, true);                   \
+    else if (fixed3 && !dbg) OCCL_LAUNCH_RASTER(G, OCCL_TILE3_W, OCCL_TILE3_H, false);          \
+    else if (fixed3) OCCL_LAUNCH_RASTER(G, OCCL_TILE3_W, OCCL_TILE3_H, true);                   \
     else OCCL_LAUNCH_RASTER(G, 0, 0, true);                                                     \
   } while (0)
   const bool dbg = out.alphas || out.pix_to_face || out.bary || out.nhits;

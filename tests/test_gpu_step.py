@@ -524,3 +524,28 @@ def test_dataset_generator_writes_reference_layout(cuda_lib, tmp_path):
             occl = cv2.imread(str(run / "Occl" / f"{j}.png"), cv2.IMREAD_UNCHANGED)
             depth = cv2.imread(str(run / "Depth" / f"{j}.png"), cv2.IMREAD_UNCHANGED)
             assert occl.shape == (64, 64) and depth.shape == (64, 64) and depth.max() > 40
+
+
+def test_compile_time_tiles_match_oracle_at_128(oracle, cuda_lib):
+    """The three compile-time tiles (32x32 default, 32x16 for 3-4 objects, 128x4 for dense meshes) on the same frame."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    sc = default_scene("teapot")
+    S = 128
+    _, _, C, R, T = oracle.pose_step(np.zeros(2, np.float32), 0.15, 1.5, 4.0)
+    ref = oracle.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
+    Rt, Tt, Ct = (torch.tensor(x[None], device="cuda").contiguous() for x in (R, T, C))
+    for tw, th in [(32, 32), (32, 16), (128, 4)]:
+        for dbg in (True, False):
+            eng = OcclusionEngine(sc, 1, RasterConfig(image_size=S, tile_w=tw, tile_h=th), debug_outputs=dbg)
+            eng.render(Rt, Tt, Ct)
+            eng.check_status()
+            assert np.array_equal(eng.obs[0, 3].cpu().numpy(), ref.zbuf), (tw, th, dbg)
+            np.testing.assert_allclose(eng.obs[0, 0].cpu().numpy(), ref.obs[0], rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(eng.occl[0].cpu().numpy(), ref.occl, rtol=RTOL, atol=4e-6)
+            np.testing.assert_allclose(float(eng.loss[0]), float(ref.loss), rtol=RTOL, atol=1e-6)
+            assert np.array_equal(eng.n_covered[0].cpu().numpy(), ref.n_covered)
+            assert np.array_equal(eng.n_visible[0].cpu().numpy(), ref.n_visible)
+            if dbg:
+                assert np.array_equal(eng.pix_to_face[0].cpu().numpy(), ref.pix_to_face), (tw, th)
+                assert np.array_equal(eng.nhits[0].cpu().numpy(), ref.nhits), (tw, th)
+                np.testing.assert_allclose(eng.alphas[0].cpu().numpy(), ref.alphas, rtol=RTOL, atol=ATOL_A)
