@@ -186,3 +186,16 @@ def reward_and_grad(scene, S, action, el0, az0, radius, prev_loss, mass, s, blur
     g = a.grad if a.grad is not None else torch.zeros_like(a)
     reward = (prev_loss - loss_val) / mass
     return reward, loss_val, (-g / mass).numpy(), alphas.numpy()
+
+
+def loss_and_pose_grad(scene, S, el0, az0, radius, s, blur, sigma, K=100, dtype=torch.float64):
+    """loss and d loss / d (elevation, azimuth) at the step-convention pose (``environment.py:363-368``) by autograd."""
+    verts = torch.tensor(scene.verts, dtype=dtype)
+    faces = torch.tensor(scene.faces, dtype=torch.long)
+    el = torch.tensor(float(el0), dtype=dtype, requires_grad=True)
+    az = torch.tensor(float(az0), dtype=dtype, requires_grad=True)
+    _, _, C, R, T = pose_step(torch.zeros(2, dtype=dtype), el, az, torch.tensor(float(radius), dtype=dtype))
+    loss_val, _ = occlusion_loss(verts, faces, scene.obj_face_start, scene.obj_vert_start, S, R, T, s, blur, sigma, K,
+                                 backward=True)
+    g = [float(t.grad) if t.grad is not None else 0.0 for t in (el, az)]
+    return loss_val, np.asarray(g, np.float64)

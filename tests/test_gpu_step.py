@@ -89,6 +89,26 @@ def test_golden_fixture_near_camera_cut_faces(cuda_lib):
     np.testing.assert_allclose(float(eng.loss[0]), float(g["loss"]), rtol=RTOL, atol=1e-6)
 
 
+@pytest.mark.parametrize("occ", ["teapot", "box"])
+def test_pose_gradient_golden_fixture(cuda_lib, occ):
+    """d loss / d (el, az) of the differentiable step against tests/golden/grad_*_128.npz (float64 autograd), 1e-3."""
+    g = np.load(os.path.join(GOLD, f"grad_{occ}_128.npz"))
+    poses, want = g["poses"], g["dloss_del_daz"]
+    n = len(poses)
+    eng = _engine(default_scene(occ), n, 128)
+    eng.reset(radius=4.0, azimuth=torch.tensor(poses[:, 0].copy()), elevation=torch.tensor(poses[:, 1].copy()))
+    mass = eng.object_mass.cpu().numpy().astype(np.float64)
+    eng.step(torch.zeros(n, 2, device="cuda"), with_grad=True)   # zero action: the pose stays, grad_action = step * d reward / d (el, az)
+    eng.check_status()
+    got = -eng.grad_action.cpu().numpy().astype(np.float64) * mass[:, None] / 0.05
+    for k in range(n):
+        scale = np.abs(want[k]).max()
+        if scale < 1e-3:
+            assert np.abs(got[k]).max() < 1e-3, (k, got[k])
+        else:
+            assert np.abs(got[k] - want[k]).max() <= 1e-3 * scale, (k, got[k], want[k])
+
+
 def test_trajectory_matches_oracle_state_machine(oracle, cuda_lib):
     """reset + several steps for a batch of envs: reward / done / loss / state, every step."""
     sc = default_scene("teapot")

@@ -225,3 +225,15 @@ def test_oracle_reproduces_near_camera_golden(oracle):
     assert np.array_equal(r.nhits.astype(np.int16), g["nhits"])
     assert np.array_equal(r.n_covered, g["n_covered"]) and np.array_equal(r.n_visible, g["n_visible"])
     assert np.float32(r.loss) == g["loss"]
+
+
+def test_pose_gradient_golden(oracle):
+    """tests/golden/grad_*_128.npz (d loss / d (el, az)) is what the dense float64 formulation gives."""
+    from oracle import dense_torch as D
+    g = np.load(os.path.join(GOLD, "grad_box_128.npz"))
+    az, el = (float(v) for v in g["poses"][2])
+    loss, grad = D.loss_and_pose_grad(default_scene("box"), 128, el, az, 4.0, float(oracle.PROJ_SCALE), float(oracle.BLUR_RADIUS),
+                                      float(oracle.SIGMA))
+    np.testing.assert_allclose(grad, g["dloss_del_daz"][2], rtol=1e-9)
+    gold = np.load(os.path.join(GOLD, "scene_box_128.npz"))
+    np.testing.assert_allclose(loss, float(gold["loss2"]), rtol=1e-5)

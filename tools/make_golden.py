@@ -76,3 +76,14 @@ np.savez_compressed(os.path.join(out_dir, "scene_teapot_near_64.npz"), C=C, R=R,
                     bary=r.bary.astype(np.float32), loss=np.float32(r.loss), nhits=r.nhits.astype(np.int16),
                     n_covered=r.n_covered.astype(np.int32), n_visible=r.n_visible.astype(np.int32))
 print("near camera: loss", r.loss, "nhits max", r.nhits.max(), "covered", r.n_covered, "visible", r.n_visible)
+
+# d loss / d (elevation, azimuth) at the poses of the two scene fixtures, float64 autograd of the dense
+# formulation; stored next to the fixtures
+for occ in ("teapot", "box"):
+    sc = default_scene(occ)
+    g = []
+    for az, el in POSES:
+        loss_d, gd = D.loss_and_pose_grad(sc, 128, el, az, 4.0, float(O.PROJ_SCALE), float(O.BLUR_RADIUS), float(O.SIGMA))
+        g.append(gd)
+        print(occ, "pose", (az, el), "loss", loss_d, "dloss/d(el,az)", gd)
+    np.savez_compressed(os.path.join(out_dir, f"grad_{occ}_128.npz"), poses=np.asarray(POSES, np.float32), dloss_del_daz=np.asarray(g))
