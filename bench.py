@@ -171,18 +171,116 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class Harness:
+    """Timing helpers shared by the legs: barrier + synchronize on both sides, CUDA events on the launching stream,
+    max over ranks."""
+
+    def __init__(self, world, dev):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.world, self.dev = torch, dist, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        self.barrier()
+        return ms
+
+
+def raster_kernel_ms(eng, actions_dev, grad, steps, warm):
+    """Average duration of the rasteriser launches (face setup + raster + clip) of one step: CUDA events around
+    occl_raster on the launching stream, the transition driven through the split C-ABI."""
+    import torch
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(warm):
+        eng.step_staged(actions_dev[i % len(actions_dev)], with_grad=grad)
+    torch.cuda.synchronize()
+    for i in range(steps):
+        eng.step_staged(actions_dev[i % len(actions_dev)], with_grad=grad, raster_events=evs[i])
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+
+def c3_scenes(n_distinct):
+    from occlusionenv_b200.meshes import procedural_scene
+    return [procedural_scene(s, n_obj=3, subdiv=5) for s in range(n_distinct)]
+
+
+def run_config3(h, dev, n_envs, steps, warm):
+    """BASELINE config 3: per-env procedural meshes of three 20 480-face objects (ShapeNet layout), 256x256."""
+    import numpy as np
+    import torch
+    from occlusionenv_b200.config import RasterConfig
+    from occlusionenv_b200.engine import OcclusionEngine
+    S, n_distinct = 256, 64
+    scenes = c3_scenes(n_distinct)
+    # engine with per-env mesh slots; the 64 distinct scenes are replicated on the device (every env still reads
+    # ITS OWN 1.1 MB of vertices and faces from HBM, which is what the algorithmic bytes count)
+    eng = OcclusionEngine(None, n_envs, RasterConfig(image_size=S), device=dev, per_env_scenes=scenes, replicate_scenes=True)
+    g = torch.Generator().manual_seed(0)
+    az = -0.5 + torch.rand(n_envs, generator=g)
+    eng.reset(radius=4.0, azimuth=az, elevation=0.1)
+    a = torch.randn(2, n_envs, 2, generator=g)
+    acts = torch.stack([a[0], -a[0], a[1], -a[1]]).to(dev)
+
+    def step(i):
+        eng.step(acts[i % 4])
+
+    for i in range(warm):
+        step(i)
+    ms = h.timed(step, steps)
+    kms = raster_kernel_ms(eng, acts, False, max(3, steps // 4), 1)
+    V, F = int(eng.c.n_verts), int(eng.c.n_faces)
+    bpe = S * S * 20 + 32 + 12 * (V + F)
+    peak, _ = _peak()
+    ach = n_envs * bpe / (kms * 1e-3) / 1e9
+    out = {"value": n_envs * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warm,
+           "envs": n_envs, "image_size": S, "faces_per_env": F, "verts_per_env": V, "objects": 3,
+           "distinct_scenes": n_distinct, "tile": [int(eng.c.tile_w), int(eng.c.tile_h)],
+           "workspace_gb": eng.workspace.numel() / 2 ** 30, "status_or": int(eng.check_status(raise_on=0)),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "kernel_ms": kms, "algorithmic_bytes_per_env_step": bpe},
+           "workload": "config 3: 3 x 20480-face procedural meshes per env (ShapeNet layout), 256x256, forward render + reward"}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload on ONE host core (scalar port): ~12-25 s
-        n_env = 96 if args.size <= 128 else 24
-        v, ms = cpu_reference_run(args.occluder, args.size, 1, n_env, 1, 0)
+        # bounded sample of the same workload on ONE host core (scalar port): one warm-up pass, one timed pass
+        n_env = 32 if args.size <= 128 else 8
+        v, ms = cpu_reference_run(args.occluder, args.size, 1, n_env, 1, 1)
         cpu_base = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                    "sample": f"{n_env} env-steps of the same workload, sequential SimpleVecEnv loop on 1 core "
-                              "(oracle port of the pytorch3d-naive CPU path)"}
+                    "sample": f"{n_env} env-steps of the same workload (after {n_env} warm-up env-steps), sequential "
+                              "SimpleVecEnv loop on 1 core (oracle port of the pytorch3d-naive CPU path)"}
 
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
@@ -193,6 +291,7 @@ def run_ours(args, rank, world, local_rank):
     from occlusionenv_b200.SubProcVecEnv import BatchedOcclusionVecEnv
     from occlusionenv_b200.config import RasterConfig
 
+    h = Harness(world, dev)
     N, S, K, W = args.envs, args.size, args.steps, args.warmup
     cfg = RasterConfig(image_size=S, tile_w=args.tile_w, tile_h=args.tile_h)
     venv = BatchedOcclusionVecEnv(N, data=args.occluder, img_size=S, device=dev, auto_reset=False, cfg=cfg,
@@ -205,27 +304,6 @@ def run_ours(args, rank, world, local_rank):
     def reset():
         eng.reset(radius=4.0, azimuth=az, elevation=el)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
-        return ms
-
     grad = bool(args.grad)
 
     # ---- (1) device-resident throughput: the fused C-ABI chain, inputs already in HBM -----------------
@@ -237,113 +315,114 @@ def run_ours(args, rank, world, local_rank):
         dev_step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_total = timed(dev_step, K)
-    clocks = sampler.stop()
-    status = int(eng.status.max().item())
+    ms_total = h.timed(dev_step, K)
     value = world * N * K / (ms_total * 1e-3)
+    # the same measurement over a longer region (>= 20 warm-up and >= 100 timed steps), so that the clock
+    # sampler sees a loaded GPU for more than a few samples whatever K the caller asked for
+    LW, LK = max(W, 20), max(K, 100)
+    for i in range(LW):
+        dev_step(i)
+    ms_long = h.timed(dev_step, LK)
+    clocks = sampler.stop()
+    status = int(eng.check_status(raise_on=0))
+    long_run = {"value": world * N * LK / (ms_long * 1e-3), "unit": UNIT, "steps": LK, "warmup": LW,
+                "ms_per_step": ms_long / LK}
 
     # ---- (2) the rasteriser alone (dominant kernel), CUDA events around its launch -------------------
     reset()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    for i in range(min(W, 3)):
-        eng.step_staged(actions_dev[i % 8], with_grad=grad)
-    torch.cuda.synchronize()
-    for i in range(K):
-        eng.step_staged(actions_dev[i % 8], with_grad=grad, raster_events=evs[i])
-    torch.cuda.synchronize()
-    raster_ms = sum(a.elapsed_time(b) for a, b in evs) / K
+    raster_ms = raster_kernel_ms(eng, actions_dev, grad, K, min(W, 3))
 
     # ---- (3) end to end through the public API: host actions in, host rewards/dones out ---------------
     reset()
     rew_host = torch.empty(N, dtype=torch.float32).pin_memory()
     done_host = torch.empty(N, dtype=torch.uint8).pin_memory()
 
-    def e2e_step(i):
+    def e2e_step(i, env=venv):
         a = actions_pinned[i % 8]
         if grad:
             a = a.to(dev, non_blocking=True).requires_grad_(True)
-        obs, rews, dones, infos = venv.step(a)
+        obs, rews, dones, infos = env.step(a)
         rew_host.copy_(rews.detach(), non_blocking=True)
-        done_host.copy_(eng.done, non_blocking=True)
+        done_host.copy_(env.engine.done, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the learner needs reward/done before the next action
 
     for i in range(min(W, 3)):
         e2e_step(i)
-    ms_e2e = timed(e2e_step, K)
+    ms_e2e = h.timed(e2e_step, K)
     e2e_value = world * N * K / (ms_e2e * 1e-3)
+    e2e_extra = {}
+    if world == 1 and not grad:
+        # (3b) the same with the auto-reset of SimpleVecEnv.step_wait enabled (masked device-side reset every step)
+        venv.auto_reset = True
+        for i in range(3):
+            e2e_step(i)
+        ms_ar = h.timed(e2e_step, K)
+        venv.auto_reset = False
+        e2e_extra["auto_reset"] = {"value": N * K / (ms_ar * 1e-3), "unit": UNIT, "ms_per_step": ms_ar / K,
+                                   "note": "as e2e, plus the masked device-side auto-reset of finished envs in every step"}
+        # (3c) a host-side consumer of the observations (datasetGenerator.py, SimpleVecEnv users on the CPU): the
+        # whole (N,4,S,S) observation batch is copied to pinned host memory every step as well
+        reset()
+        obs_host = torch.empty(N, 4, S, S, dtype=torch.float32).pin_memory()
+        kk = max(3, min(K, 10))
 
-    # ---- (4) optional: learner-boundary gather over NVLink (config 5) ---------------------------------
+        def e2e_obs_step(i):
+            obs, rews, dones, infos = venv.step(actions_pinned[i % 8])
+            obs_host.copy_(obs, non_blocking=True)
+            rew_host.copy_(rews, non_blocking=True)
+            done_host.copy_(eng.done, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_obs_step(0)
+        ms_o = h.timed(e2e_obs_step, kk)
+        e2e_extra["obs_to_host"] = {"value": N * kk / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o / kk, "steps": kk,
+                                    "d2h_bytes_per_step": N * (4 * S * S * 4 + 5),
+                                    "note": "observations copied to pinned host memory every step too (PCIe bound)"}
+        del obs_host
+
+    # ---- (4) learner-boundary exchange over NVLink (config 5): 8192 envs per GPU, by default when world > 1 -----------
     gather = None
-    if world > 1 and args.gather:
-        from occlusionenv_b200.dist import LearnerGather
-        obs_bytes = (world - 1) * N * (4 * S * S * 4 + 5)
-        # (a) serial: step all envs, then gather (obs, reward, done) to rank 0
-        lg = LearnerGather(N, (4, S, S), dev, dst=0)
+    if world > 1 and not args.no_gather and not grad:
+        gather = run_gather_legs(h, args, rank, world, dev, K, W)
+
+    # ---- (5) the other BASELINE configurations, N = 1 only --------------------------------------------------------------
+    config_results = None
+    if world == 1 and not args.no_configs and not grad and args.size == 128 and args.occluder == "box":
+        config_results = {}
+        # config 4: differentiable step, same scene and batch
+        ck = max(K, 20)
         reset()
 
-        def gather_step(i):
-            eng.step(actions_dev[i % 8], with_grad=False)
-            lg.gather(eng.obs, eng.reward, eng.done)
+        def grad_step(i):
+            eng.step(actions_dev[i % 8], with_grad=True)
 
-        for i in range(min(W, 3)):
-            gather_step(i)
-        ms_g = timed(gather_step, K)
-        gather = {"serial": {"value": world * N * K / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / K},
-                  "bytes_to_learner_per_step": obs_bytes, "collective": "gather(obs,reward,done)->rank0 (NCCL over NVLink)"}
-        del lg
-        # (b) double-buffered: the envs of a rank form two half batches; while half A's observations travel to the
-        # learner (NCCL on a side stream) half B renders.  Same work and same bytes per step, on-policy per half.
-        from occlusionenv_b200.engine import OcclusionEngine
-        from occlusionenv_b200.meshes import default_scene
-        H = N // 2
-        sc = default_scene(args.occluder)
-        halves = [OcclusionEngine(sc, H, cfg, device=dev) for _ in range(2)]
-        for h, e2 in enumerate(halves):
-            e2.reset(radius=4.0, azimuth=az[h * H:(h + 1) * H], elevation=el[h * H:(h + 1) * H])
-        lgs = [LearnerGather(H, (4, S, S), dev, dst=0) for _ in range(2)]
-        comm = torch.cuda.Stream(device=dev)
-        rendered = [torch.cuda.Event() for _ in range(2)]
-        gathered = [torch.cuda.Event() for _ in range(2)]
-        main = torch.cuda.current_stream()
-
-        def gather_step_db(i):
-            a = actions_dev[i % 8]
-            for h in range(2):
-                main.wait_event(gathered[h])            # half h's buffers are free again
-                halves[h].step(a[h * H:(h + 1) * H].contiguous(), with_grad=False)
-                rendered[h].record(main)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(rendered[h])
-                    lgs[h].gather(halves[h].obs, halves[h].reward, halves[h].done)
-                    gathered[h].record(comm)
-
-        for h in range(2):
-            gathered[h].record(comm)
-        for i in range(min(W, 3)):
-            gather_step_db(i)
-        main.wait_stream(comm)
-
-        def db_and_drain(i):
-            gather_step_db(i)
-            if i == K - 1:
-                main.wait_stream(comm)
-
-        ms_db = timed(db_and_drain, K)
-        gather["double_buffered"] = {"value": world * N * K / (ms_db * 1e-3), "unit": UNIT, "ms_per_step": ms_db / K,
-                                     "note": "two half batches per rank; gather of one half overlaps the render of the other"}
-        gather["value"] = gather["double_buffered"]["value"]
-        gather["unit"] = UNIT
+        for i in range(max(W, 5)):
+            grad_step(i)
+        ms_g = h.timed(grad_step, ck)
+        kms_g = raster_kernel_ms(eng, actions_dev, True, ck, 3)
+        peak, _ = _peak()
+        bpe_g = algorithmic_bytes_per_env_step(S, True)
+        ach_g = N * bpe_g / (kms_g * 1e-3) / 1e9
+        config_results["c4_grad"] = {
+            "value": N * ck / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g / ck, "steps": ck, "warmup": max(W, 5),
+            "envs": N, "image_size": S, "status_or": int(eng.check_status(raise_on=0)),
+            "roofline": {"bound": "hbm", "achieved": ach_g, "peak": peak, "unit": "GB/s", "frac": ach_g / peak,
+                         "kernel_ms": kms_g, "algorithmic_bytes_per_env_step": bpe_g},
+            "workload": "config 4: teapot + box occluder, 4096 envs, 128x128, differentiable step (fwd + gradient to the action)"}
+        # config 3: dense per-env meshes at the BASELINE shape (8192 envs x 256^2); the C2 engine is released first
+        del venv, eng
+        torch.cuda.empty_cache()
+        try:
+            config_results["c3_dense"] = run_config3(h, dev, args.c3_envs, max(3, min(K, args.c3_steps)), 2)
+        except Exception as ex:  # reported, never silently dropped
+            config_results["c3_dense"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = _peak()
     bpe = algorithmic_bytes_per_env_step(S, grad)
     achieved = N * bpe / (raster_ms * 1e-3) / 1e9
     traffic = None
@@ -352,20 +431,24 @@ def run_ours(args, rank, world, local_rank):
         t = json.load(open(tp))
         if t.get("envs") == N and t.get("size") == S and t.get("occluder") == args.occluder and bool(t.get("grad")) == grad:
             traffic = t.get("dram_bytes_per_launch")
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 2 * 4, "d2h_bytes_per_step": N * 5,
+           "ms_per_step": ms_e2e / K,
+           "note": "BatchedOcclusionVecEnv.step(pinned host actions) -> rewards+dones copied to pinned host, stream sync "
+                   "every step; observations stay in HBM for the policy, as in the reference (device tensors)"}
+    e2e.update(e2e_extra)
     line = {
         "metric": METRIC if not grad else "env-steps/sec (render+reward, fwd+bwd)", "value": value, "unit": UNIT,
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "envs_per_gpu": N, "image_size": S, "occluder": args.occluder,
-                   "faces": int(eng.c.n_faces), "faces_per_pixel": 100, "tile": [int(eng.c.tile_w), int(eng.c.tile_h)],
+                   "faces": 2476 if args.occluder == "box" else 4928, "faces_per_pixel": 100, "tile": [32, 32],
                    "l2": "outputs (obs+occlusion map: %.0f MB/step/GPU) larger than L2; no flush needed" % (N * S * S * 20 / 1e6),
-                   "auto_reset": "excluded", "status_or": status},
+                   "auto_reset": "excluded (see e2e.auto_reset)", "status_or": status},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 2 * 4, "d2h_bytes_per_step": N * 5,
-                "ms_per_step": ms_e2e / K,
-                "note": "BatchedOcclusionVecEnv.step(pinned host actions) -> rewards+dones copied to pinned host, stream sync "
-                        "every step; observations stay in HBM for the policy, as in the reference (device tensors)"},
-        "gpu_launches": 6 * K,  # pose, project, face_setup, raster, raster_clip (cut faces; CTAs leave at once otherwise), finalize
+        "long_run": long_run,
+        "e2e": e2e,
+        # pose, project, face_setup, raster, raster_clip (cut faces; CTAs leave at once otherwise), finalize
+        "gpu_launches": 6 * K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "raster_kernel", "kernel_ms": raster_ms,
                      "kernel_share_of_step": raster_ms / (ms_total / K),
@@ -375,22 +458,125 @@ def run_ours(args, rank, world, local_rank):
     }
     if gather is not None:
         line["gather"] = gather
+    if config_results is not None:
+        line["config_results"] = config_results
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_gather_legs(h, args, rank, world, dev, K, W):
+    """BASELINE config 5: `--gather-envs` (8192) envs per GPU, step + delivery of obs / reward / done to the learner rank.
+    Four ways to deliver (all leave rank-ordered (N_total, ...) tensors in the learner's HBM):
+      serial           step, then ONE grouped NCCL transfer (no staging copy: the rasteriser renders into the send
+                       buffer; on the learner into its slice of the gathered tensor)
+      double_buffered  two half batches per rank; the transfer of one half (side stream) overlaps the render of the other
+      p2p_fused        the rasteriser's epilogue stores the observation rows straight into the learner's HBM over NVLink
+                       (peer-mapped gather buffer); only reward + done (5 B/env) go through NCCL
+      p2p_fused_gray   the same with the compact 2-plane observation (grey + depth: the reference's R = G = B)"""
+    import torch
+    from occlusionenv_b200.config import RasterConfig
+    from occlusionenv_b200.dist import LearnerGather
+    from occlusionenv_b200.engine import OcclusionEngine
+    from occlusionenv_b200.meshes import default_scene
+    N, S = args.gather_envs, args.size
+    sc = default_scene(args.occluder)
+    az, el, actions_host = make_poses(N, 0, offset=rank * 1000003)
+    actions_dev = actions_host.to(dev)
+    warm = min(W, 3)
+    out = {"envs_per_gpu": N, "envs_total": N * world, "image_size": S,
+           "collective": "obs/reward/done of every rank -> learner rank 0 over NVLink"}
+
+    def leg(name, planes, transport, halves):
+        cfg = RasterConfig(image_size=S, obs_planes=planes)
+        H = N // halves
+        engs = [OcclusionEngine(sc, H, cfg, device=dev) for _ in range(halves)]
+        for k, e in enumerate(engs):
+            e.reset(radius=4.0, azimuth=az[k * H:(k + 1) * H], elevation=el[k * H:(k + 1) * H])
+        lgs = [LearnerGather(H, (planes, S, S), dev, dst=0, transport=transport) for _ in range(halves)]
+        bufs = [lg.obs_send_buffer() for lg in lgs]
+        main = torch.cuda.current_stream()
+        if halves == 1:
+            def step(i):
+                engs[0].step(actions_dev[i % 8], obs=bufs[0])
+                lgs[0].gather(bufs[0], engs[0].reward, engs[0].done)
+        else:
+            comm = torch.cuda.Stream(device=dev)
+            rendered = [torch.cuda.Event() for _ in range(halves)]
+            gathered = [torch.cuda.Event() for _ in range(halves)]
+            for k in range(halves):
+                gathered[k].record(comm)
+
+            def step(i):
+                a = actions_dev[i % 8]
+                for k in range(halves):
+                    main.wait_event(gathered[k])            # half k's buffers are free again
+                    engs[k].step(a[k * H:(k + 1) * H].contiguous(), obs=bufs[k])
+                    rendered[k].record(main)
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(rendered[k])
+                        lgs[k].gather(bufs[k], engs[k].reward, engs[k].done)
+                        gathered[k].record(comm)
+                if i == -1:
+                    main.wait_stream(comm)
+        for i in range(warm):
+            step(i)
+        if halves > 1:
+            main.wait_stream(comm)
+
+        def timed_step(i):
+            step(i)
+            if halves > 1 and i == K - 1:
+                main.wait_stream(comm)
+
+        ms = h.timed(timed_step, K)
+        nbytes = (world - 1) * N * (planes * S * S * 4 + 5)
+        out[name] = {"value": world * N * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "obs_planes": planes,
+                     "transport": transport, "bytes_to_learner_per_step": nbytes,
+                     "learner_ingest_gbs": nbytes / (ms / K * 1e-3) / 1e9}
+        del engs, lgs, bufs
+        torch.cuda.empty_cache()
+
+    def step_only():
+        e = OcclusionEngine(sc, N, RasterConfig(image_size=S), device=dev)
+        e.reset(radius=4.0, azimuth=az, elevation=el)
+
+        def s(i):
+            e.step(actions_dev[i % 8])
+
+        for i in range(warm):
+            s(i)
+        ms = h.timed(s, K)
+        out["step_only"] = {"value": world * N * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K}
+
+    step_only()
+    leg("serial", 4, "nccl", 1)
+    leg("double_buffered", 4, "nccl", 2)
+    for name, planes in (("p2p_fused", 4), ("p2p_fused_gray", 2)):
+        try:
+            leg(name, planes, "p2p", 1)
+        except Exception as ex:  # CUDA IPC unavailable (e.g. a container without peer access): reported, not hidden
+            out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    best = max((v["value"] for k, v in out.items() if isinstance(v, dict) and "value" in v and k != "step_only"), default=None)
+    out["value"], out["unit"] = best, UNIT
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--occluder", default="box", choices=["box", "teapot"])
     ap.add_argument("--grad", action="store_true", help="differentiable step (config 4)")
-    ap.add_argument("--gather", action="store_true", help="also time step + NCCL gather to rank 0 (config 5)")
+    ap.add_argument("--no-gather", action="store_true", help="world > 1: skip the learner-boundary legs (config 5)")
+    ap.add_argument("--gather-envs", type=int, default=8192, help="envs per GPU of the config-5 legs")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip config_results (config 4 and config 3)")
+    ap.add_argument("--c3-envs", type=int, default=8192)
+    ap.add_argument("--c3-steps", type=int, default=20)
     ap.add_argument("--tile-w", type=int, default=0)
     ap.add_argument("--tile-h", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

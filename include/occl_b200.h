@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCCL_ABI_VERSION 1
+#define OCCL_ABI_VERSION 2
 #define OCCL_MAX_OBJ 4
 #define OCCL_CAM_STRIDE 48 /* floats per env in the camera block, see occl_pose_* */
 
@@ -68,6 +68,13 @@ typedef struct OcclConfig {
   float reward_step;                        /* -0.2; environment.py:392 (stored as +0.2, subtracted) */
   int32_t debug_exact;                      /* 1: evaluate every (pixel, face) pair with the reference's exact
                                                operation sequence (no guarded fast path); for parity tests */
+  int32_t ws_budget_mb;                     /* cap, in MiB, of the rasteriser's per-face scratch inside the workspace
+                                               (0 = 2048): the batch is rasterised in chunks of as many envs as fit,
+                                               so the workspace does not grow as N x F (occl_workspace_bytes) */
+  int32_t obs_planes;                       /* 0 / 4: obs is (N,4,S,S) R, G, B, depth -- the reference's layout
+                                               (environment.py:376-378); 2: (N,2,S,S) grey, depth -- the same
+                                               information (flat shading of white vertices gives R = G = B) in half
+                                               the bytes, for transport to the learner (occlusionenv_b200/dist.py) */
 } OcclConfig;
 
 /* Scene mesh in HBM. verts: (V,3) f32 world coordinates, faces: (F,3) i32 into verts.
@@ -97,10 +104,13 @@ typedef struct OcclWorkspace {
 
 /* Outputs. Pointers marked [opt] may be NULL. */
 typedef struct OcclOutputs {
-  float* obs;            /* (N,4,S,S) flat-shaded RGB + depth(-1 bg); environment.py:375-378       */
+  float* obs;            /* (N,4,S,S) flat-shaded RGB + depth(-1 bg); environment.py:375-378
+                            ((N,2,S,S) grey + depth with OcclConfig.obs_planes = 2); may be PEER memory:
+                            the rows are stored by the rasteriser's epilogue wherever this points              */
   float* occl;           /* (N,S,S)  alpha of self.image = sum_{i<j} A_i A_j; environment.py:373   */
   float* reward;         /* (N,)     environment.py:382-392   (not written by occl_reset)          */
-  uint8_t* done;         /* (N,)     environment.py:386       (occl_reset: loss <= threshold)      */
+  uint8_t* done;         /* (N,)     environment.py:386   (occl_reset without a mask: loss <= threshold;
+                                     a masked occl_reset does not write it, so it may alias env_mask)       */
   float* loss;           /* (N,)     new self.fullReward; environment.py:381,384                   */
   float* position;       /* (N,3)    camera centre; info['position'], environment.py:363-365       */
   int32_t* n_covered;    /* (N,n_obj) px hard-covered by object i rendered alone (exact)           */
@@ -111,6 +121,9 @@ typedef struct OcclOutputs {
   int32_t* pix_to_face;  /* [opt] (N,S,S)  scene K=1 fragments.pix_to_face (packed face index)     */
   float* bary;           /* [opt] (N,S,S,3) scene K=1 barycentrics (-1 on background)              */
   int32_t* nhits;        /* [opt] (N,n_obj,S,S) soft hits per pixel before the K cut               */
+  uint32_t* status_or;   /* [opt] (1,) running OR of every status word written through this struct:
+                            ORed into, never cleared, by occl_finalize / occl_step / occl_reset / occl_render
+                            (the caller zeroes it when it has looked) -- one word to check instead of (N,) */
 } OcclOutputs;
 
 int occl_abi_version(void);
@@ -127,7 +140,8 @@ int occl_selftest_div(unsigned long long n_samples, unsigned long long seed, uns
 /* Fill tile_w/tile_h when they are 0 and validate the configuration. */
 int occl_config_resolve(OcclConfig* cfg, int with_grad);
 
-/* Scratch bytes for n_envs environments (camera blocks, projected vertices, tile partials). */
+/* Scratch bytes for n_envs environments: camera blocks, projected vertices and tile partials for all of them,
+ * plus the per-face scratch of one chunk of envs (see OcclConfig.ws_budget_mb). */
 size_t occl_workspace_bytes(const OcclConfig* cfg, int n_envs, int with_grad);
 
 /* Byte offsets inside the workspace of: camera blocks (N,OCCL_CAM_STRIDE) f32, projected vertices
@@ -149,7 +163,9 @@ int occl_pose_lookat(const OcclConfig* cfg, int n_envs, OcclState state, float* 
 int occl_pose_set(int n_envs, const float* R, const float* T, const float* C, float* cam, void* stream);
 
 /* MeshRasterizer.transform (world -> view -> NDC, z := view z) for every env and vertex.
- * vproj (N,V,4) f32 = (x_ndc, y_ndc, z_view, 0); vtan [opt] (N,V,4) = d(x,y)/d_el, d(x,y)/d_az. */
+ * vproj (N,V,4) f32 = (x_ndc, y_ndc, z_view, 0); vtan [opt] (N,V,4) = d(x,y)/d_el, d(x,y)/d_az.
+ * status [opt] (N,): zeroed here -- a transition driven through the split entry points starts with this call
+ * (occl_raster then ORs its flags in); pass the same array as OcclOutputs.status. */
 int occl_project(const OcclConfig* cfg, int n_envs, const float* cam, OcclScene scene, float* vproj,
                  float* vtan, uint32_t* status, void* stream);
 
@@ -173,7 +189,8 @@ int occl_step(const OcclConfig* cfg, int n_envs, const float* action, OcclScene 
  * elevation/azimuth/radius have been written into `state` by the caller.
  * env_mask [opt] (N,) u8: only environments with a non-zero entry are reset, the others keep their
  * state and outputs untouched -- the auto-reset of SimpleVecEnv.step_wait (SubProcVecEnv.py:211-214)
- * without a host round trip (pass the `done` output of occl_step). */
+ * without a host round trip (pass the `done` output of occl_step; a masked reset leaves `out.done` alone,
+ * so mask and output may be the same array). */
 int occl_reset(const OcclConfig* cfg, int n_envs, const uint8_t* env_mask, OcclScene scene, OcclState state,
                OcclWorkspace ws, OcclOutputs out, void* stream);
 

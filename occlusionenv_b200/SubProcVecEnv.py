@@ -126,7 +126,10 @@ class SimpleVecEnv(VecEnv):
 
 class LazyInfos(Sequence):
     """``infos`` of a batched step: behaves like the reference's ``list[dict]`` but builds a dict only
-    when an element is read (65 536 Python dicts per step would dominate the step time)."""
+    when an element is read (65 536 Python dicts per step would dominate the step time).  Everything in it is
+    the TERMINAL step's result, also for envs that the same call auto-reset (``SubProcVecEnv.py:210-214``): the
+    masked reset renders into scratch outputs, so the engine's occlusion map / loss / counts / position are
+    still the step's.  ``full_state`` is a view of the engine's occlusion map, valid until the next step."""
 
     def __init__(self, venv, terminal_obs=None, done=None):
         self._v = venv
@@ -166,6 +169,11 @@ class BatchedOcclusionVecEnv(VecEnv):
       ``keep_terminal_obs=True`` to get ``info['terminal_observation']`` (costs one host sync).
     * ``reset()``: azimuth ~ U(-40, 40) radians per env (the reference's range, ``SubProcVecEnv.py:233``),
       from a seedable generator; returns (N,4,S,S).
+    * ``scene_sampler``: a callable returning a ``SceneMesh`` (stand-in for the ShapeNet loader,
+      ``environment.py:91-198``) gives every env its OWN meshes and the reference's ``new_scene`` behaviour
+      (``environment.py:292-298,327-328``): ``reset()`` draws a new scene per env and redraws, up to 10 times,
+      the envs whose reset render shows no occlusion (loss <= 0.1); with ``resample_on_auto_reset=True`` the
+      auto-reset inside ``step`` does the same for the finished envs (one host sync per step to learn which).
     * Returned tensors are views of the engine's output buffers, valid until the next call
       (pass ``copy_outputs=True`` to get fresh tensors like the reference).
     """
@@ -173,12 +181,18 @@ class BatchedOcclusionVecEnv(VecEnv):
     def __init__(self, num_envs: int, data=None, img_size: int = 512, device: Optional[str] = None,
                  auto_reset: bool = True, keep_terminal_obs: bool = False, copy_outputs: bool = False,
                  reset_azimuth_range=(-40.0, 40.0), cfg: Optional[RasterConfig] = None, env_offset: int = 0,
-                 per_env_scenes: Optional[list] = None):
+                 per_env_scenes: Optional[list] = None, scene_sampler=None, resample_on_auto_reset: bool = False,
+                 max_resets: int = 10):
         self.img_size = img_size
         self.device = torch.device(device or "cuda:0")
         cfg = cfg or RasterConfig(image_size=img_size)
         if cfg.image_size != img_size:
             raise ValueError("cfg.image_size and img_size disagree")
+        self.scene_sampler = scene_sampler
+        self.resample_on_auto_reset = bool(resample_on_auto_reset) and scene_sampler is not None
+        self.max_resets = int(max_resets)
+        if scene_sampler is not None and per_env_scenes is None:
+            per_env_scenes = [scene_sampler() for _ in range(num_envs)]
         scene = per_env_scenes[0] if per_env_scenes is not None else resolve_scene(data)
         self.engine = OcclusionEngine(scene, num_envs, cfg, device=str(self.device), per_env_scenes=per_env_scenes)
         super().__init__(num_envs, Box(0, 1, shape=(4, img_size, img_size)), Box(low=-0.1, high=0.1, shape=(2,)))
@@ -200,13 +214,31 @@ class BatchedOcclusionVecEnv(VecEnv):
         self._gen.manual_seed(int(seed) + self.env_offset)
         return [seed + self.env_offset + i for i in range(self.num_envs)]
 
-    def reset(self, radius=4.0, azimuth=None, elevation=0.0):
+    def reset(self, radius=4.0, azimuth=None, elevation=0.0, new_scene: bool = True):
         if azimuth is None:
             lo, hi = self.reset_azimuth_range
             azimuth = lo + (hi - lo) * torch.rand(self.num_envs, generator=self._gen)
-        self.engine.reset(radius=radius, azimuth=azimuth, elevation=elevation)
+        eng = self.engine
+        if self.scene_sampler is not None and new_scene:
+            eng.set_env_scenes(range(self.num_envs), [self.scene_sampler() for _ in range(self.num_envs)])
+        eng.reset(radius=radius, azimuth=azimuth, elevation=elevation)
+        if self.scene_sampler is not None and new_scene:
+            self._redraw_unoccluded(torch.ones(self.num_envs, dtype=torch.bool, device=self.device))
         self.actions = None
-        return self._out(self.engine.obs)
+        return self._out(eng.obs)
+
+    def _redraw_unoccluded(self, candidates: torch.Tensor, scratch_outputs: bool = False):
+        """``environment.py:327-328``: an env whose reset render shows no occlusion (loss <= 0.1) gets another
+        scene, at most ``max_resets`` renders in all; the pose stays what the reset set."""
+        eng = self.engine
+        for _ in range(self.max_resets - 1):
+            again = candidates & ~(eng.full_reward > eng.c.done_threshold)
+            ids = torch.nonzero(again).flatten().tolist()  # host sync, as the reference's `if loss > 0.1`
+            if not ids:
+                return
+            eng.set_env_scenes(ids, [self.scene_sampler() for _ in ids])
+            eng.reset(mask=again.to(torch.uint8), scratch_outputs=scratch_outputs)
+            candidates = again
 
     def step_async(self, actions):
         if self.actions is not None:
@@ -227,21 +259,25 @@ class BatchedOcclusionVecEnv(VecEnv):
             eng.step(a.contiguous())
             rewards = self._out(eng.reward)
         dones = eng.done.bool()
-        terminal = None
-        infos = None
         if self.auto_reset:
-            if self.keep_terminal_obs:
-                infos = LazyInfos(self, eng.obs.clone(), dones.clone())
-            else:
-                infos = LazyInfos(self, None, None)
-            # masked device-side reset of the finished envs; `done` itself is the mask
-            done_mask = eng.done.clone()
-            eng.reset(radius=4.0, azimuth=0.0, elevation=0.0, mask=done_mask)
-            eng.done.copy_(done_mask)
-            eng.loss.copy_(infos._loss)
+            infos = LazyInfos(self, eng.obs.clone() if self.keep_terminal_obs else None, dones)
+            # masked device-side reset of the finished envs; `done` itself is the mask.  Only obs and the env state
+            # change: the step's occlusion map, loss, counts, position and done stay in place for `infos`.
+            if self.resample_on_auto_reset:
+                ids = torch.nonzero(dones).flatten().tolist()
+                if ids:
+                    eng.set_env_scenes(ids, [self.scene_sampler() for _ in ids])
+            eng.reset(radius=4.0, azimuth=0.0, elevation=0.0, mask=eng.done, scratch_outputs=True)
+            if self.resample_on_auto_reset and ids:
+                self._redraw_unoccluded(dones, scratch_outputs=True)
         else:
             infos = LazyInfos(self, None, None)
         return self._out(eng.obs), rewards, dones, infos
+
+    def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP) -> int:
+        """Flags raised by ANY env in ANY transition since the last check (the kernels keep a running OR on the
+        device, so the hot loop never syncs for it); raises ``OcclError`` on the ones that mean a wrong result."""
+        return self.engine.check_status(raise_on)
 
     def close(self):
         pass

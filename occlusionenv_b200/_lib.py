@@ -6,7 +6,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
-OCCL_ABI_VERSION = 1
+OCCL_ABI_VERSION = 2
 OCCL_MAX_OBJ = 4
 OCCL_CAM_STRIDE = 48
 
@@ -30,7 +30,7 @@ class OcclConfig(Structure):
         ("blur_radius", c_float), ("sigma", c_float), ("proj_scale", c_float), ("z_clip", c_float),
         ("step_size", c_float), ("light", c_float * 3),
         ("done_threshold", c_float), ("reward_done", c_float), ("reward_step", c_float),
-        ("debug_exact", c_int32),
+        ("debug_exact", c_int32), ("ws_budget_mb", c_int32), ("obs_planes", c_int32),
     ]
 
 
@@ -52,7 +52,8 @@ class OcclOutputs(Structure):
     _fields_ = [("obs", c_void_p), ("occl", c_void_p), ("reward", c_void_p), ("done", c_void_p),
                 ("loss", c_void_p), ("position", c_void_p), ("n_covered", c_void_p),
                 ("n_visible", c_void_p), ("status", c_void_p), ("grad_action", c_void_p),
-                ("alphas", c_void_p), ("pix_to_face", c_void_p), ("bary", c_void_p), ("nhits", c_void_p)]
+                ("alphas", c_void_p), ("pix_to_face", c_void_p), ("bary", c_void_p), ("nhits", c_void_p),
+                ("status_or", c_void_p)]
 
 
 # every symbol include/occl_b200.h declares

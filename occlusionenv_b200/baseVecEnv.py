@@ -8,6 +8,7 @@ never raises the errors; here ``step_wait`` without a pending ``step_async`` doe
 from __future__ import annotations
 
 import abc
+import inspect
 import math
 import pickle
 from typing import Iterable, List, Optional, Sequence, Union
@@ -134,7 +135,8 @@ class VecEnvWrapper(VecEnv):
         self.venv = venv
         super().__init__(venv.num_envs, observation_space or venv.observation_space,
                          action_space or venv.action_space)
-        self.class_attributes = dict(vars(type(self)))
+        # every member of the class INCLUDING inherited ones (the reference uses inspect.getmembers, baseVecEnv.py:247)
+        self.class_attributes = dict(inspect.getmembers(type(self)))
 
     def step_async(self, actions):
         self.venv.step_async(actions)

@@ -34,6 +34,9 @@ class RasterConfig:
     tile_w: int = 0                              # CTA tile (0 = automatic)
     tile_h: int = 0
     debug_exact: bool = False                    # every pair through the reference-order arithmetic (tests)
+    obs_planes: int = 4                          # 4: (N,4,S,S) RGB + depth (reference); 2: grey + depth (compact transport)
+    ws_budget_mb: int = 0                        # cap of the rasteriser's per-face scratch in MiB (0 = 2048): envs are
+                                                 # rasterised in chunks that fit it, see occl_b200.h
 
     @property
     def blur_radius(self) -> float:

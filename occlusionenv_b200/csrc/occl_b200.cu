@@ -253,6 +253,7 @@ __global__ void project_kernel(long long total, int V, const float* __restrict__
   const int e = (int)(idx / V);
   if (env_mask && !env_mask[e]) return;
   const int v = (int)(idx - (long long)e * V);
+  if (status && v == 0) status[e] = 0u;  // a new transition of env e starts here (face_setup_kernel ORs its flags in later)
   const float* __restrict__ c = cam + (size_t)e * OCCL_CAM_STRIDE;
   const float* __restrict__ p = verts + (size_t)e * verts_stride + (size_t)v * 3;
   const float x = __ldg(p + 0), y = __ldg(p + 1), z = __ldg(p + 2);
@@ -306,6 +307,7 @@ struct RasterParams {
   const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
   // outputs
   float* obs;
+  int obs_planes;  // 4: R, G, B, depth planes (reference layout) ; 2: grey, depth (compact transport layout)
   float* occl;
   float* alphas;
   int* pix_to_face;
@@ -861,27 +863,66 @@ __device__ __forceinline__ int obj_of_face(const RasterParams& p, int f) {
   return o;
 }
 
-// soft accumulator word: low 32 bits = running product of (1 - prob) as float bits,
-// high 32 bits = hit count (bits 0..19) | count of "weak" hits with 1 - prob > 1/4, saturating at 511
-//                (bits 20..28) | member of the current selection round (bit 29; the low word is then the
-//                write cursor of the pixel's hit list) | top-K resolved flag (bit 30) | hard-covered flag (bit 31)
+// soft accumulator of a (pixel, object) slot: two 32-bit words, updated with NATIVE shared-memory atomics
+// (ATOMS.ADD / ATOMS.OR; a 64-bit or floating-point shared atomic is a compare-and-swap loop on sm_100a):
+//   low word  = L, the sum over the hits of -log2(1 - prob) in fixed point with SOFT_FRAC fractional bits
+//               (integer adds commute, so the per-pixel product -- and alpha -- is run-to-run deterministic);
+//               once the top-K rule has been applied (SOFT_RESOLVED) the low word holds the float bits of the
+//               product itself; during a selection round (SOFT_ROUND) it is the write cursor of the hit list
+//   high word = hit count (bits 0..19) | SOFT_RESOLVED (bit 20) | SOFT_ROUND (bit 21) | SOFT_COVERED (bit 22)
+//               | count of "strong" hits, factor 1 - prob <= 1/4 (bits 23..31; wraps off the top of the word,
+//               which can only lose the strong-hit shortcut, never fake it)
+// Terms are clamped to SOFT_TERM_MAX = 26 (a factor below 2^-26 makes alpha == 1.0f on its own) and a slot with
+// SOFT_STRONG_NEEDED strong hits is 1.0f whatever L says, so L <= 12 * 26 + 128 * 2 < 2^(32 - SOFT_FRAC) never wraps
+// where it is read.
 #define SOFT_CNT_MASK 0xfffffu
-#define SOFT_WEAK_MASK 0x1ffu
-#define SOFT_WEAK_SHIFT 20
-#define SOFT_ROUND 0x20000000u
-#define SOFT_RESOLVED 0x40000000u
+#define SOFT_RESOLVED 0x00100000u
+#define SOFT_ROUND 0x00200000u
+#define SOFT_COVERED 0x00400000u
+#define SOFT_STRONG_SHIFT 23
+#define SOFT_STRONG_ONE (1u << SOFT_STRONG_SHIFT)
+#define SOFT_FRAC 22
+#define SOFT_TERM_MAX 26.0f
 #define SOFT_STRONG_NEEDED 13  // 0.25^13 < 2^-25: that many strong factors make 1 - product == 1.0f exactly
-__device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float q, bool covered) {
-  unsigned long long old = *slot, assumed;
-  do {
-    assumed = old;
-    const float pr = __uint_as_float((unsigned)(assumed & 0xffffffffull)) * q;
-    unsigned hi = (unsigned)(assumed >> 32);
-    hi += (q > 0.25f && ((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK) != SOFT_WEAK_MASK) ? 1u + (1u << SOFT_WEAK_SHIFT) : 1u;
-    if (covered) hi |= 0x80000000u;
-    const unsigned long long nw = ((unsigned long long)hi << 32) | (unsigned long long)__float_as_uint(pr);
-    old = atomicCAS(slot, assumed, nw);
-  } while (old != assumed);
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// -log2(1 - sigmoid(-sd / sigma)) = log2(1 + 2^(-x)), x = sd / (sigma ln 2)            (tolerance side of the path)
+//   = max(-x, 0) + log2(1 + u),  u = 2^-|x| in (0, 1].
+// log2(1 + u): MUFU.LG2 has an ABSOLUTE error of ~2^-22.6 that does not average out (a pixel just outside a far,
+// tiny object collects ~100 hits with u ~ 1e-4 each: alpha ~ 0.01 came out 3e-6 off); for u < 1/4 a degree-5
+// polynomial in u (relative error 1.4e-7, unbiased) is used instead, so the error of every weak term is relative.
+__device__ __forceinline__ float soft_term(float signed_dist, float inv_sigma_log2e) {
+  const float x = signed_dist * inv_sigma_log2e;
+  const float a = fabsf(x);
+  const float u = ex2_approx(-a);
+  float pl = __fmaf_rn(-0.1329696774482727f, u, 0.26198700070381165f);
+  pl = __fmaf_rn(pl, u, -0.35743656754493713f);
+  pl = __fmaf_rn(pl, u, 0.4807146489620209f);
+  pl = __fmaf_rn(pl, u, -0.7213436365127563f);
+  pl = __fmaf_rn(pl, u, 1.4426950216293335f);
+  const float t = u < 0.25f ? pl * u : lg2_approx(1.0f + u);
+  return fminf(x < 0.f ? t + a : t, SOFT_TERM_MAX);
+}
+__device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float term, bool covered) {
+  unsigned* w = (unsigned*)slot;
+  atomicAdd(w, __float2uint_rn(term * (float)(1u << SOFT_FRAC)));
+  atomicAdd(w + 1, term >= 2.0f ? 1u + SOFT_STRONG_ONE : 1u);
+  if (covered) atomicOr(w + 1, SOFT_COVERED);
+}
+// product of the factors of an unresolved slot from its fixed-point log sum
+__device__ __forceinline__ float soft_product(unsigned long long w) {
+  const unsigned hi = (unsigned)(w >> 32), lo = (unsigned)(w & 0xffffffffull);
+  if (hi & SOFT_RESOLVED) return __uint_as_float(lo);
+  if ((hi >> SOFT_STRONG_SHIFT) >= SOFT_STRONG_NEEDED) return 0.0f;
+  return ex2_approx(-((float)lo * (1.0f / (float)(1u << SOFT_FRAC))));
+}
+// strong-hit shortcut of the top-K rule: whatever K hits are the nearest, at most (count - strong) of them are weak
+__device__ __forceinline__ bool soft_strong_shortcut(unsigned hi, int K) {
+  const int cnt = (int)(hi & SOFT_CNT_MASK), strong = (int)(hi >> SOFT_STRONG_SHIFT);
+  return K - (cnt - strong) >= SOFT_STRONG_NEEDED;
 }
 
 __device__ __forceinline__ unsigned long long pack2f(float lo, float hi) {
@@ -968,8 +1009,7 @@ __device__ __noinline__ void raster_clip_record(const uint4* __restrict__ rec, c
     eval_clip_pixel(&st, ndc_x[lx], ndc_y[ly], blur, bbox_r, &cp);
     if (cp.soft_hit) {
       const float sd = cp.soft_inside ? -cp.soft_dist : cp.soft_dist;
-      const float prob = rcp_approx(1.0f + ex2_approx(sd * inv_sigma_log2e));
-      soft_accumulate(soft + pix, 1.0f - prob, cp.hard_hit);
+      soft_accumulate(soft + pix, soft_term(sd, inv_sigma_log2e), cp.hard_hit);
     }
     if (cp.hard_hit) {
       const unsigned low = (w10 & REC_FIDX_MASK) | KEY_CLIP | ((unsigned)cp.hard_which << 30);
@@ -1115,14 +1155,13 @@ __device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const 
     if (!inside && dist >= p.blur) continue;
     const int pix = ly * tile_w + lx;
     const float sd = inside ? -dist : dist;
-    const float prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
     bool hard_ok = false;
     if (inside) {
       const uint32_t hb = rec[11];
       hard_ok = lx >= (int)(hb & 0xff) && lx <= (int)((hb >> 8) & 0xff) && ly >= (int)((hb >> 16) & 0xff) &&
                 ly <= (int)((hb >> 24) & 0xff);
     }
-    soft_accumulate(soft + pix, 1.0f - prob, hard_ok);
+    soft_accumulate(soft + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
     if (hard_ok) {
       bool queued = false;
       if (DEFER && !have_bary) {
@@ -1147,6 +1186,7 @@ __device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const 
       const float wa = 1.f - tt, wb = tt;
       const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
       const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
+      const float prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
       const float k = prob * p.inv_sigma;
       grad_accumulate(sm.gacc + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx + pix, k * dsd_el, k * dsd_az);
     }
@@ -1246,8 +1286,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
           // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
           // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
           // reference's alpha is exactly 1.0f: no selection needed.
-          const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
-          if (p.K - weak >= SOFT_STRONG_NEEDED) {
+          if (soft_strong_shortcut(hi, p.K)) {
             sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
             if (GRAD) sm.gacc[i] = 0ull;
             atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
@@ -1280,7 +1319,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             if (r < RSLOT_CAP) {
               s_rslot[r] = i;
               s_roff[r] = (unsigned short)off;
-              const unsigned h2 = (hi & ~(SOFT_WEAK_MASK << SOFT_WEAK_SHIFT)) | SOFT_ROUND;
+              const unsigned h2 = hi | SOFT_ROUND;
               sm.soft[i] = ((unsigned long long)h2 << 32) | (unsigned long long)(unsigned)off;
               const int obj = i / tpx, pix = i - obj * tpx;
               const int ly = pix / tile_w, lx = pix - ly * tile_w;
@@ -1453,8 +1492,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       // Whatever K hits are the nearest, at most `weak` of them are weak; if the others number at least
       // SOFT_STRONG_NEEDED their factors (each <= 1/4) already push the product below 2^-25, i.e. the
       // reference's alpha is exactly 1.0f: no selection needed.
-      const int weak = (int)((hi >> SOFT_WEAK_SHIFT) & SOFT_WEAK_MASK);  // saturated = "many": no shortcut
-      if (p.K - weak >= SOFT_STRONG_NEEDED) {
+      if (soft_strong_shortcut(hi, p.K)) {
         sm.soft[i] = ((unsigned long long)(hi | SOFT_RESOLVED) << 32);  // product := +0.0f
         if (GRAD) sm.gacc[i] = 0ull;
         atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
@@ -1691,11 +1729,15 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         if (xi >= S || yi >= S) continue;
         const size_t pix = (size_t)yi * S + xi;
         *(float4*)(p.occl + (size_t)env * npix + pix) = zero4;
-        float* o = p.obs + (size_t)env * 4 * npix + pix;
+        float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
         *(float4*)(o) = one4;
-        *(float4*)(o + npix) = one4;
-        *(float4*)(o + 2 * npix) = one4;
-        *(float4*)(o + 3 * npix) = neg4;
+        if (p.obs_planes == 4) {
+          *(float4*)(o + npix) = one4;
+          *(float4*)(o + 2 * npix) = one4;
+          *(float4*)(o + 3 * npix) = neg4;
+        } else {
+          *(float4*)(o + npix) = neg4;
+        }
       }
     } else
 #pragma unroll 1
@@ -1705,8 +1747,9 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       if (xi >= S || yi >= S) continue;
       const size_t pix = (size_t)yi * S + xi;
       p.occl[(size_t)env * npix + pix] = 0.f;
-      float* o = p.obs + (size_t)env * 4 * npix + pix;
-      o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
+      float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
+      o[0] = 1.0f;
+      if (p.obs_planes == 4) { o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f; } else { o[npix] = -1.0f; }
       for (int ob = 0; ob < p.n_obj; ++ob) {
         if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
         if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
@@ -1728,7 +1771,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
 
   // ---- init accumulators -------------------------------------------------------------------
   for (int i = tid; i < tpx; i += OCCL_THREADS) sm.hard[i] = ~0ull;
-  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = (unsigned long long)__float_as_uint(1.0f);
+  for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.soft[i] = 0ull;
   if (GRAD)
     for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
@@ -1963,8 +2006,9 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         if (o < p.n_obj) touched |= (unsigned)(sm.soft[(size_t)o * tpx + i] >> 32);
       if (touched == 0u && key == ~0ull) {
         p.occl[(size_t)env * npix + pix] = 0.f;
-        float* o = p.obs + (size_t)env * 4 * npix + pix;
-        o[0] = 1.0f; o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f;
+        float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
+        o[0] = 1.0f;
+        if (p.obs_planes == 4) { o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f; } else { o[npix] = -1.0f; }
         for (int ob = 0; ob < p.n_obj; ++ob) {
           if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
           if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
@@ -1984,10 +2028,10 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       PR[o] = 1.f;
       if (o < p.n_obj) {
         const unsigned long long w = sm.soft[(size_t)o * tpx + i];
-        PR[o] = __uint_as_float((unsigned)(w & 0xffffffffull));
+        PR[o] = soft_product(w);
         A[o] = 1.0f - PR[o];
         const unsigned hi = (unsigned)(w >> 32);
-        ncov[o] += (int)(hi >> 31);
+        ncov[o] += (int)((hi / SOFT_COVERED) & 1u);
         if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + o) * npix + pix] = A[o];
         if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + o) * npix + pix] = (int)(hi & SOFT_CNT_MASK);
       }
@@ -2043,11 +2087,15 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       const float texel = (b0 + b1) + b2;
       rgb = sh.x * texel + sh.y;
     }
-    float* o = p.obs + (size_t)env * 4 * npix + pix;
+    float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
     o[0] = rgb;
-    o[npix] = rgb;
-    o[2 * npix] = rgb;
-    o[3 * npix] = depth;
+    if (p.obs_planes == 4) {
+      o[npix] = rgb;
+      o[2 * npix] = rgb;
+      o[3 * npix] = depth;
+    } else {
+      o[npix] = depth;
+    }
     if (DBG && p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = pf;
     if (DBG && p.bary) {
       float* bq = p.bary + ((size_t)env * npix + pix) * 3;
@@ -2113,11 +2161,20 @@ __global__ void finalize_kernel(int n, int mode, int n_tiles, int n_obj, int nor
                                 float done_threshold, float reward_done, float reward_step, float step_size,
                                 const Partial* __restrict__ partials, const float* __restrict__ action,
                                 float* __restrict__ full_reward, float* __restrict__ object_mass,
-                                float* __restrict__ reward, uint8_t* __restrict__ done,
+                                float* __restrict__ reward, uint8_t* done,
                                 float* __restrict__ loss_out, int* __restrict__ n_covered,
                                 int* __restrict__ n_visible, float* __restrict__ grad_action,
-                                const uint8_t* __restrict__ env_mask) {
+                                const uint32_t* __restrict__ status, uint32_t* __restrict__ status_or,
+                                const uint8_t* env_mask) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (status_or) {
+    // running OR of every status word this library has produced (one warp reduction, one atomic when non-zero):
+    // the host checks ONE word, when it wants to, instead of scanning (N,) words after every step
+    const bool on = e < n && !(env_mask && !env_mask[e]);
+    const unsigned st = on ? status[e] : 0u;
+    const unsigned all = __reduce_or_sync(0xffffffffu, st);
+    if (all && (threadIdx.x & 31) == 0) atomicOr(status_or, all);
+  }
   if (e >= n) return;
   if (env_mask && !env_mask[e]) return;
   double loss = 0.0, objsq = 0.0, g0 = 0.0, g1 = 0.0;
@@ -2137,7 +2194,8 @@ __global__ void finalize_kernel(int n, int mode, int n_tiles, int n_obj, int nor
   if (mode == 1) {
     full_reward[e] = lossf;                                                  // :323
     object_mass[e] = (norm_with_object_size ? (float)objsq : lossf) + 1.0f;  // :324
-    if (done) done[e] = (uint8_t)(!(lossf > done_threshold));                // :327 (no occlusion at reset)
+    // :327 (no occlusion at reset).  Not written by a masked reset: the mask usually IS the `done` array of the step.
+    if (done && !env_mask) done[e] = (uint8_t)(!(lossf > done_threshold));
     return;
   }
   const float mass = object_mass[e];
@@ -2180,10 +2238,24 @@ static int cuda_fail(cudaError_t e, const char* where) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Raise a kernel's dynamic shared-memory limit once per device (not on every launch).
+template <void (*KERNEL)(const RasterParams)>
+static cudaError_t ensure_dyn_smem(size_t smem) {
+  static size_t have[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && have[dev] >= smem) return cudaSuccess;
+  e = cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) have[dev] = smem;
+  return e;
+}
+
 struct WsLayout {
   size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, total;
   int tidx_cap;
   int n_tiles;
+  int chunk;  // envs rasterised per launch: the per-face scratch (geo .. tile_cnt) is sized for this many, not for N
 };
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
@@ -2234,6 +2306,7 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   if (c->n_obj < 1 || c->n_obj > OCCL_MAX_OBJ) return OCCL_E_INVALID;
   if (c->n_verts < 1 || c->n_faces < 1) return OCCL_E_INVALID;
   if (c->faces_per_pixel < 1 || c->faces_per_pixel > 128) return OCCL_E_INVALID;
+  if (c->obs_planes != 0 && c->obs_planes != 2 && c->obs_planes != 4) return OCCL_E_INVALID;
   if (c->n_faces >= (1 << 28)) return OCCL_E_INVALID;  // packed face index field
   if (c->obj_face_start[0] != 0 || c->obj_face_start[c->n_obj] != c->n_faces) return OCCL_E_INVALID;
   for (int i = 0; i < c->n_obj; ++i)
@@ -2254,23 +2327,37 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
   return OCCL_OK;
 }
 
+// Per-env buffers (camera, projected vertices, tile partials) are sized for all N envs; the per-FACE scratch of the
+// rasteriser (live-face records, pixel ranges, lighting, tile index lists: ~90 B per face plus 4 B per tile-list slot,
+// of which only the live / touched part is ever written) is sized for a CHUNK of envs and reused chunk after chunk on
+// the stream (face_setup -> raster -> raster_clip per chunk).  The chunk is the largest env count whose scratch fits
+// ws_budget_mb (default 2 GiB): 4096 envs x 2 476 faces (config 2) is one chunk, 8192 envs x 61 440 faces x 256^2
+// (config 3; 78 GB if sized for N) runs in chunks of ~220 envs.
 static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   const int tx = (c->image_size + c->tile_w - 1) / c->tile_w;
   const int ty = (c->image_size + c->tile_h - 1) / c->tile_h;
   L->n_tiles = tx * ty;
+  L->tidx_cap = c->n_faces < 8192 ? c->n_faces : 8192;
+  const size_t per_env = (size_t)c->n_faces * (sizeof(uint4) * 5 + sizeof(float2)) + sizeof(int) * (size_t)L->n_tiles * (L->tidx_cap + 1) +
+                         sizeof(int) + sizeof(uint32_t) * TILE_MASK_WORDS;
+  const size_t budget = (size_t)(c->ws_budget_mb > 0 ? c->ws_budget_mb : 2048) << 20;
+  size_t chunk = budget / per_env;
+  if (chunk < 1) chunk = 1;
+  if (chunk > (size_t)n) chunk = (size_t)n;
+  L->chunk = (int)chunk;
+  const size_t m = chunk;
   size_t off = 0;
   L->cam = off;      off = align_up(off + sizeof(float) * OCCL_CAM_STRIDE * (size_t)n, 256);
   L->vproj = off;    off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
   L->vtan = off;     if (with_grad) off = align_up(off + sizeof(float4) * (size_t)n * c->n_verts, 256);
   L->partials = off; off = align_up(off + sizeof(Partial) * (size_t)n * L->n_tiles, 256);
-  L->geo = off;      off = align_up(off + sizeof(uint4) * 4 * (size_t)n * c->n_faces, 256);
-  L->rng = off;      off = align_up(off + sizeof(uint4) * (size_t)n * c->n_faces, 256);
-  L->n_live = off;   off = align_up(off + sizeof(int) * (size_t)n, 256);
-  L->tile_mask = off; off = align_up(off + sizeof(uint32_t) * TILE_MASK_WORDS * (size_t)n, 256);
-  L->shade = off;    off = align_up(off + sizeof(float2) * (size_t)n * c->n_faces, 256);
-  L->tidx_cap = c->n_faces < 8192 ? c->n_faces : 8192;
-  L->tile_idx = off; off = align_up(off + sizeof(int) * (size_t)n * L->n_tiles * L->tidx_cap, 256);
-  L->tile_cnt = off; off = align_up(off + sizeof(int) * (size_t)n * L->n_tiles, 256);
+  L->geo = off;      off = align_up(off + sizeof(uint4) * 4 * m * c->n_faces, 256);
+  L->rng = off;      off = align_up(off + sizeof(uint4) * m * c->n_faces, 256);
+  L->n_live = off;   off = align_up(off + sizeof(int) * m, 256);
+  L->tile_mask = off; off = align_up(off + sizeof(uint32_t) * TILE_MASK_WORDS * m, 256);
+  L->shade = off;    off = align_up(off + sizeof(float2) * m * c->n_faces, 256);
+  L->tile_idx = off; off = align_up(off + sizeof(int) * m * L->n_tiles * L->tidx_cap, 256);
+  L->tile_cnt = off; off = align_up(off + sizeof(int) * m * L->n_tiles, 256);
   L->total = off;
   return 0;
 }
@@ -2385,36 +2472,58 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.faces = sc.faces; p.faces_stride = sc.faces_env_stride;
   p.cam = (const float*)(base + L.cam);
   p.partials = (Partial*)(base + L.partials);
-  p.obs = out.obs; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
+  p.obs = out.obs; p.obs_planes = c.obs_planes == 2 ? 2 : 4; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
   p.nhits = out.nhits; p.status = out.status; p.env_mask = mask;
   const size_t smem = tile_smem_bytes(&c, grad);
-  const long long blocks = (long long)n * L.n_tiles;
-  if (blocks > 0x7fffffffLL) return OCCL_E_INVALID;
-  {
-    SetupParams sp;
-    sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
-    sp.z_clip = c.z_clip; sp.status = out.status; sp.grad = grad;
-    sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
-    sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
-    sp.tile_mask = (uint32_t*)(base + L.tile_mask);
-    sp.tile_idx = p.tile_idx; sp.tile_cnt = bin ? (int*)(base + L.tile_cnt) : nullptr; sp.tidx_cap = L.tidx_cap;
-    sp.shade = (float2*)(base + L.shade);
-    sp.verts = sc.verts; sp.verts_stride = sc.verts_env_stride; sp.cam = p.cam;
-    sp.light[0] = c.light[0]; sp.light[1] = c.light[1]; sp.light[2] = c.light[2];
-    sp.n_obj = c.n_obj;
-    for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
-    sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
-    sp.inv_tile_w = 1.0f / (float)c.tile_w; sp.inv_tile_h = 1.0f / (float)c.tile_h;
-    if (bin) face_setup_kernel<true><<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
-    else face_setup_kernel<false><<<n, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
-    CK(cudaGetLastError(), "face_setup_kernel");
-  }
+  if ((long long)L.chunk * L.n_tiles > 0x7fffffffLL) return OCCL_E_INVALID;
+  SetupParams sp;
+  sp.S = c.image_size; sp.V = c.n_verts; sp.F = c.n_faces; sp.cull = c.cull_backfaces; sp.bbox_r = p.bbox_r;
+  sp.z_clip = c.z_clip; sp.status = out.status; sp.grad = grad;
+  sp.vproj = p.vproj; sp.faces = sc.faces; sp.faces_stride = sc.faces_env_stride;
+  sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.env_mask = mask;
+  sp.tile_mask = (uint32_t*)(base + L.tile_mask);
+  sp.tile_idx = p.tile_idx; sp.tile_cnt = bin ? (int*)(base + L.tile_cnt) : nullptr; sp.tidx_cap = L.tidx_cap;
+  sp.shade = (float2*)(base + L.shade);
+  sp.verts = sc.verts; sp.verts_stride = sc.verts_env_stride; sp.cam = p.cam;
+  sp.light[0] = c.light[0]; sp.light[1] = c.light[1]; sp.light[2] = c.light[2];
+  sp.n_obj = c.n_obj;
+  for (int i = 0; i <= OCCL_MAX_OBJ; ++i) sp.obj_face_start[i] = p.obj_face_start[i];
+  sp.tile_w = c.tile_w; sp.tile_h = c.tile_h; sp.tiles_x = p.tiles_x; sp.n_tiles = L.n_tiles;
+  sp.inv_tile_w = 1.0f / (float)c.tile_w; sp.inv_tile_h = 1.0f / (float)c.tile_h;
   const bool fixed = c.tile_w == OCCL_TILE_W && c.tile_h == OCCL_TILE_H;
   const bool fixed2 = !fixed && c.tile_w == OCCL_TILE2_W && c.tile_h == OCCL_TILE2_H;
   const bool fixed3 = !fixed && !fixed2 && c.tile_w == OCCL_TILE3_W && c.tile_h == OCCL_TILE3_H;
+  const bool dbg = out.alphas || out.pix_to_face || out.bary || out.nhits;
+  const size_t npix = (size_t)c.image_size * c.image_size;
+  const RasterParams p0 = p;
+  // chunk after chunk of envs through the same per-face scratch (see ws_layout): every per-env array is entered at
+  // the chunk's first env, so that the kernels index everything by the env's position inside the chunk
+  for (int e0 = 0; e0 < n; e0 += L.chunk) {
+    const int m = n - e0 < L.chunk ? n - e0 : L.chunk;
+    const size_t e = (size_t)e0;
+    p.vproj = p0.vproj + e * c.n_verts;
+    p.vtan = p0.vtan ? p0.vtan + e * c.n_verts : nullptr;
+    p.verts = p0.verts + e * (size_t)p0.verts_stride;
+    p.faces = p0.faces + e * (size_t)p0.faces_stride;
+    p.cam = p0.cam + e * OCCL_CAM_STRIDE;
+    p.partials = p0.partials + e * L.n_tiles;
+    p.obs = p0.obs + e * p0.obs_planes * npix;
+    p.occl = p0.occl + e * npix;
+    p.alphas = p0.alphas ? p0.alphas + e * c.n_obj * npix : nullptr;
+    p.pix_to_face = p0.pix_to_face ? p0.pix_to_face + e * npix : nullptr;
+    p.bary = p0.bary ? p0.bary + e * npix * 3 : nullptr;
+    p.nhits = p0.nhits ? p0.nhits + e * c.n_obj * npix : nullptr;
+    p.status = p0.status + e;
+    p.env_mask = p0.env_mask ? p0.env_mask + e : nullptr;
+    sp.vproj = p.vproj; sp.faces = p.faces; sp.verts = p.verts; sp.cam = p.cam; sp.status = p.status;
+    sp.env_mask = p.env_mask;
+    const long long blocks = (long long)m * L.n_tiles;
+    if (bin) face_setup_kernel<true><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    else face_setup_kernel<false><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    CK(cudaGetLastError(), "face_setup_kernel");
 #define OCCL_LAUNCH_RASTER(G, W, H, D)                                                                                   \
   do {                                                                                                                   \
-    CK(cudaFuncSetAttribute(raster_kernel<G, W, H, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr"); \
+    CK((ensure_dyn_smem<raster_kernel<G, W, H, D>>(smem)), "smem attr");                                                  \
     raster_kernel<G, W, H, D><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
   } while (0)
 #define OCCL_LAUNCH_RASTER_G(G)                                                                 \
@@ -2427,19 +2536,19 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     else if (fixed3) OCCL_LAUNCH_RASTER(G, OCCL_TILE3_W, OCCL_TILE3_H, true);                   \
     else OCCL_LAUNCH_RASTER(G, 0, 0, true);                                                     \
   } while (0)
-  const bool dbg = out.alphas || out.pix_to_face || out.bary || out.nhits;
-  if (grad) OCCL_LAUNCH_RASTER_G(true); else OCCL_LAUNCH_RASTER_G(false);
+    if (grad) OCCL_LAUNCH_RASTER_G(true); else OCCL_LAUNCH_RASTER_G(false);
 #undef OCCL_LAUNCH_RASTER_G
-  // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile
-  if (grad) {
-    CK(cudaFuncSetAttribute(raster_clip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    raster_clip_kernel<true><<<(unsigned)n, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
-  } else {
-    CK(cudaFuncSetAttribute(raster_clip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
-    raster_clip_kernel<false><<<(unsigned)n, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
-  }
 #undef OCCL_LAUNCH_RASTER
-  CK(cudaGetLastError(), "raster_kernel");
+    // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile
+    if (grad) {
+      CK(ensure_dyn_smem<raster_clip_kernel<true>>(smem), "smem attr");
+      raster_clip_kernel<true><<<(unsigned)m, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+    } else {
+      CK(ensure_dyn_smem<raster_clip_kernel<false>>(smem), "smem attr");
+      raster_clip_kernel<false><<<(unsigned)m, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+    }
+    CK(cudaGetLastError(), "raster_kernel");
+  }
   return OCCL_OK;
 }
 
@@ -2464,7 +2573,7 @@ static int finalize_impl(const OcclConfig* cfg, int n, int mode, const float* ac
   finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       n, mode, L.n_tiles, c.n_obj, c.norm_with_object_size, c.done_threshold, c.reward_done, c.reward_step, c.step_size,
       (const Partial*)(base + L.partials), action, st.full_reward, st.object_mass, out.reward, out.done, out.loss,
-      out.n_covered, out.n_visible, mode == 0 ? out.grad_action : nullptr, mask);
+      out.n_covered, out.n_visible, mode == 0 ? out.grad_action : nullptr, out.status, out.status_or, mask);
   CK(cudaGetLastError(), "finalize_kernel");
   return OCCL_OK;
 }

@@ -61,7 +61,7 @@ def write_params(run_dir: str, rows: np.ndarray) -> None:
 
 def generate_dataset(out_dir: str = "./Dataset", num_obj: int = 10000, num_frame: int = 20, img_size: int = 512,
                      lr: float = 2.5e-2, azimuth: float = 0.0, batch: int = 256, data=None, seed: Optional[int] = None,
-                     device: Optional[str] = None, first_run: int = 0) -> int:
+                     device: Optional[str] = None, first_run: int = 0, max_step_factor: int = 5) -> int:
     """Writes runs ``first_run .. first_run + num_obj - 1``; returns the number of frames written.
     Every run: reset(azimuth) then ``num_frame`` differentiable steps with action = lr * randn(2)."""
     import torch
@@ -82,8 +82,15 @@ def generate_dataset(out_dir: str = "./Dataset", num_obj: int = 10000, num_frame
             dirs.append(d)
         rows = np.zeros((n, num_frame, 5), np.float64)
         eng = venv.engine
-        for j in range(num_frame):
-            action = torch.nn.Parameter((lr * torch.randn(n, 2, generator=gen)).to(venv.device))
+        # per-run frame counter: a step whose gradient is not finite is REPEATED with the same action and the frame
+        # index does not advance (the reference's `continue`, datasetGenerator.py:93-94), so every run ends with
+        # exactly num_frame frames and num_frame rows; runs that are complete keep stepping unobserved
+        j_of = np.zeros(n, np.int64)
+        action_val = (lr * torch.randn(n, 2, generator=gen)).to(venv.device)
+        for _ in range(max_step_factor * num_frame):
+            if (j_of >= num_frame).all():
+                break
+            action = torch.nn.Parameter(action_val.clone())
             obs, reward, finished, info = venv.step(action)
             reward.sum().backward()
             eng.check_status()
@@ -91,12 +98,18 @@ def generate_dataset(out_dir: str = "./Dataset", num_obj: int = 10000, num_frame
             obs_h = obs.detach().cpu().numpy()
             occl_h = eng.occl.detach().cpu().numpy()
             el, az = eng.elevation.cpu().numpy(), eng.azimuth.cpu().numpy()
-            for i in range(n):
-                if not np.isfinite(grad[i]).all():   # the reference skips a frame whose gradient is NaN (:95-96)
-                    continue
+            ok = np.isfinite(grad).all(axis=1)
+            for i in np.nonzero(ok & (j_of < num_frame))[0]:
+                j = int(j_of[i])
                 rows[i, j] = (j, el[i], az[i], grad[i, 0], grad[i, 1])
                 write_frame(dirs[i], j, obs_h[i], occl_h[i])
                 frames += 1
+            j_of[ok] += 1
+            fresh = (lr * torch.randn(n, 2, generator=gen)).to(venv.device)  # a new action only after a kept frame
+            action_val = torch.where(torch.from_numpy(ok).to(venv.device)[:, None], fresh, action_val)
+        else:
+            if not (j_of >= num_frame).all():
+                raise RuntimeError("generate_dataset: gradient stayed non-finite for some run")
         for i in range(n):
             write_params(dirs[i], rows[i])
         del venv

@@ -1,7 +1,24 @@
-"""Multi-GPU plumbing: contiguous env sharding (no communication inside the step) and the one
-collective at the learner boundary: gather observations / rewards / dones of all
-ranks to the PPO learner rank, rank order = env order.  One process per GPU, ``torch.distributed`` with
-NCCL over NVLink on the GPU box (gloo in the CPU tests)."""
+"""Multi-GPU plumbing: contiguous env sharding (no communication inside the step) and the one exchange at the
+learner boundary: observations / rewards / dones of all ranks to the PPO learner rank, rank
+order = env order -- the ``torch.stack`` of ``/root/reference/SubProcVecEnv.py:219`` across GPUs.  One process per
+GPU, ``torch.distributed`` with NCCL over NVLink on the GPU box (gloo in the CPU tests).
+
+Two transports for the observations, both without a staging copy:
+
+* ``transport="nccl"``: ONE grouped NCCL operation (``batch_isend_irecv`` = one ncclGroup) moves obs + reward + done
+  of every rank straight into the rank's slice of the learner's contiguous (N_total, ...) buffers.  The rasteriser
+  renders into ``obs_send_buffer()`` -- on the learner rank that IS its slice of the gathered tensor.
+* ``transport="p2p"``: the learner's gather buffer is mapped into every env rank's address space (CUDA IPC over
+  NVLink / NVSwitch peer memory) and ``obs_send_buffer()`` returns the rank's slice of THAT: the rasteriser's epilogue
+  stores every observation row directly into the learner's HBM while the tile is being finished -- compute and
+  transfer are one kernel, there is no collective for the observations at all.  ``gather()`` then only moves
+  reward + done (5 B/env), which, being stream-ordered after the step, also tells the learner that the rows landed.
+
+The transfer is bound by the learner GPU's NVLink ingest (measured peer copy 770 GB/s per direction,
+B200_PROFILING.md): 262 144 B/env at 128^2.  ``planes=2`` (OcclConfig.obs_planes) halves it: the reference's R = G = B
+(flat shading of white vertices) travel once as a grey plane next to the depth plane; ``expand_compact_obs`` restores
+(N, 4, S, S) on the learner.
+"""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -31,38 +48,126 @@ def scatter_actions(actions_all: Optional[torch.Tensor], n_local: int, src: int 
     return out
 
 
+def expand_compact_obs(obs2: torch.Tensor) -> torch.Tensor:
+    """(N, 2, S, S) grey + depth -> the reference's (N, 4, S, S) RGB + depth (``environment.py:376-378``)."""
+    return obs2[:, (0, 0, 0, 1)]
+
+
+def _share_cuda_tensor(t: Optional[torch.Tensor], src: int):
+    """Map ``t`` (allocated on rank ``src``) into every other rank's address space through CUDA IPC; returns a
+    tensor aliasing the same device memory (peer access over NVLink).  On ``src`` it is ``t`` itself."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    box = [reduce_tensor(t) if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    if dist.get_rank() == src:
+        return t
+    fn, args = box[0]
+    return fn(*args)
+
+
 class LearnerGather:
-    """Pre-allocated gather of (obs, reward, done) to the learner rank.
+    """Pre-allocated exchange of (obs, reward, done) to the learner rank; see the module docstring.
 
-    ``gather()`` issues ``dist.gather`` (NCCL: a grouped send/recv over NVLink) for the three tensors;
-    on the learner the results land in rank-major order, i.e. global env order.  ``all_gather()`` is the
-    variant in which every rank receives everything (``ncclAllGather``)."""
+    ``gather()`` returns, on the learner, ``(obs (N_total, planes, S, S), reward (N_total,), done (N_total,) u8)`` in
+    global env order; ``(None, None, None)`` elsewhere.  ``n_buffers`` > 1 rotates the destination buffers so that
+    the learner can read step t while step t+1 is being written (``next_buffer()``)."""
 
-    def __init__(self, n_local: int, obs_shape, device, dst: int = 0):
+    def __init__(self, n_local: int, obs_shape, device, dst: int = 0, transport: str = "nccl", n_buffers: int = 1):
         self.world = dist.get_world_size()
         self.rank = dist.get_rank()
         self.dst = dst
         self.n_local = n_local
         self.device = device
         self.obs_shape = tuple(obs_shape)
-        self._bufs = None
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        self.transport = transport
+        self.n_buffers = int(n_buffers)
+        self._cur = 0
+        self._g_obs, self._g_small, self._send_obs, self._all = None, None, None, None
+        lo = self.rank * n_local
+        self._slice = slice(lo, lo + n_local)
 
-    def _alloc(self, everyone: bool):
-        if self._bufs is None and (everyone or self.rank == self.dst):
-            n = self.n_local * self.world
-            self._bufs = (torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=self.device),
-                          torch.empty(n, dtype=torch.float32, device=self.device),
-                          torch.empty(n, dtype=torch.uint8, device=self.device))
-        return self._bufs
+    # -- buffers -----------------------------------------------------------------------------------
+    def _alloc(self):
+        if self._g_small is not None:
+            return
+        n = self.n_local * self.world
+        learner = self.rank == self.dst
+        if learner:
+            self._g_obs = [torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=self.device)
+                           for _ in range(self.n_buffers)]
+            self._g_small = (torch.empty(n, dtype=torch.float32, device=self.device),
+                             torch.empty(n, dtype=torch.uint8, device=self.device))
+        else:
+            self._g_small = (None, None)
+        if self.transport == "p2p":
+            # every rank sees the learner's buffers; env ranks write their slice from inside the rasteriser
+            self._g_obs = [_share_cuda_tensor(self._g_obs[b] if learner else None, self.dst) for b in range(self.n_buffers)]
+        elif not learner:
+            self._send_obs = [torch.empty((self.n_local,) + self.obs_shape, dtype=torch.float32, device=self.device)
+                              for _ in range(self.n_buffers)]
 
+    def obs_send_buffer(self) -> torch.Tensor:
+        """Where the rasteriser should write this rank's observations (``engine.step(..., obs=...)``) so that
+        ``gather`` needs no copy: the rank's slice of the learner's buffer (learner rank, or any rank with the p2p
+        transport), else a local send buffer."""
+        self._alloc()
+        if self.transport == "p2p" or self.rank == self.dst:
+            return self._g_obs[self._cur][self._slice]
+        return self._send_obs[self._cur]
+
+    def next_buffer(self):
+        self._cur = (self._cur + 1) % self.n_buffers
+
+    # -- the exchange --------------------------------------------------------------------------------
     def gather(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
-        bufs = self._alloc(False)
+        self._alloc()
+        learner = self.rank == self.dst
+        done = done if done.dtype == torch.uint8 else done.to(torch.uint8)
+        in_place = obs.data_ptr() == self.obs_send_buffer().data_ptr()
+        g_obs = self._g_obs[self._cur] if (learner or self.transport == "p2p") else None
+        move_obs = not (self.transport == "p2p" and in_place)
+        if self.transport == "p2p" and not in_place:
+            g_obs[self._slice].copy_(obs)  # peer store of a tensor rendered elsewhere
+            move_obs = False
+        if dist.get_backend() != "nccl":
+            return self._gather_collective(obs, reward, done, move_obs)
+        ops = []
+        if learner:
+            g_rew, g_done = self._g_small
+            for r in range(self.world):
+                sl = slice(r * self.n_local, (r + 1) * self.n_local)
+                if r == self.rank:
+                    if move_obs and not in_place:
+                        g_obs[sl].copy_(obs)
+                    g_rew[sl].copy_(reward)
+                    g_done[sl].copy_(done)
+                    continue
+                if move_obs:
+                    ops.append(dist.P2POp(dist.irecv, g_obs[sl], r))
+                ops.append(dist.P2POp(dist.irecv, g_rew[sl], r))
+                ops.append(dist.P2POp(dist.irecv, g_done[sl], r))
+        else:
+            if move_obs:
+                ops.append(dist.P2POp(dist.isend, obs.contiguous(), self.dst))
+            ops.append(dist.P2POp(dist.isend, reward.contiguous(), self.dst))
+            ops.append(dist.P2POp(dist.isend, done.contiguous(), self.dst))
+        for w in dist.batch_isend_irecv(ops):  # one ncclGroup: a single grouped transfer for all three tensors
+            w.wait()                           # (stream-ordered: no host block with NCCL)
+        if learner:
+            return self._g_obs[self._cur], self._g_small[0], self._g_small[1]
+        return None, None, None
+
+    def _gather_collective(self, obs, reward, done, move_obs=True):
+        """gloo (CPU tests): plain ``dist.gather`` per tensor."""
+        learner = self.rank == self.dst
         outs = []
-        for i, t in enumerate((obs, reward, done.to(torch.uint8))):
+        bufs = (self._g_obs[self._cur] if learner else None,) + tuple(self._g_small)
+        for i, t in enumerate((obs, reward, done)):
             t = t.contiguous()
-            if self.rank == self.dst:
-                lst = list(bufs[i].chunk(self.world, dim=0))
-                dist.gather(t, lst, dst=self.dst)
+            if learner:
+                dist.gather(t, list(bufs[i].chunk(self.world, dim=0)), dst=self.dst)
                 outs.append(bufs[i])
             else:
                 dist.gather(t, None, dst=self.dst)
@@ -70,7 +175,12 @@ class LearnerGather:
         return tuple(outs)
 
     def all_gather(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
-        bufs = self._alloc(True)
+        """Variant in which every rank receives everything (``ncclAllGather``)."""
+        if self._all is None:
+            n = self.n_local * self.world
+            self._all = (torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=self.device),
+                         torch.empty(n, dtype=torch.float32, device=self.device),
+                         torch.empty(n, dtype=torch.uint8, device=self.device))
         for i, t in enumerate((obs, reward, done.to(torch.uint8))):
-            dist.all_gather_into_tensor(bufs[i], t.contiguous())
-        return bufs
+            dist.all_gather_into_tensor(self._all[i], t.contiguous())
+        return self._all

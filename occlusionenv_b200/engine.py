@@ -24,7 +24,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 class OcclusionEngine:
     def __init__(self, scene, n_envs: int, cfg: RasterConfig, device="cuda:0", debug_outputs: bool = False,
-                 per_env_scenes: Optional[list] = None):
+                 per_env_scenes: Optional[list] = None, replicate_scenes: bool = False):
         if not torch.cuda.is_available():
             raise L.OcclError("OcclusionEngine needs a CUDA device (there is no CPU fallback)")
         self.lib = L.load()
@@ -32,9 +32,13 @@ class OcclusionEngine:
         self.n = int(n_envs)
         self.cfg = cfg
         self.S = cfg.image_size
+        rep_idx = None
         if per_env_scenes is not None:
             scene0 = per_env_scenes[0]
-            assert len(per_env_scenes) == self.n
+            if replicate_scenes:  # env e gets scene e % len(per_env_scenes): replicated on the device, not on the host
+                rep_idx = torch.arange(self.n) % len(per_env_scenes)
+            else:
+                assert len(per_env_scenes) == self.n
             for sc in per_env_scenes:
                 assert sc.verts.shape == scene0.verts.shape and sc.faces.shape == scene0.faces.shape
                 assert np.array_equal(sc.obj_face_start, scene0.obj_face_start)
@@ -50,6 +54,10 @@ class OcclusionEngine:
         self.n_obj = sc.n_obj
         self.verts = torch.from_numpy(np.ascontiguousarray(verts, np.float32)).to(self.device)
         self.faces = torch.from_numpy(np.ascontiguousarray(faces, np.int32)).to(self.device)
+        if rep_idx is not None:
+            rep_idx = rep_idx.to(self.device)
+            self.verts = self.verts.index_select(0, rep_idx).contiguous()
+            self.faces = self.faces.index_select(0, rep_idx).contiguous()
         c = L.OcclConfig()
         c.image_size = cfg.image_size
         c.n_obj = sc.n_obj
@@ -72,6 +80,8 @@ class OcclusionEngine:
         c.reward_done = cfg.reward_done
         c.reward_step = cfg.reward_step
         c.debug_exact = int(cfg.debug_exact)
+        c.ws_budget_mb = int(cfg.ws_budget_mb)
+        c.obs_planes = int(cfg.obs_planes)
         L.check(self.lib.occl_config_resolve(ctypes.byref(c), 1), "occl_config_resolve")
         self.c = c
         self.c_scene = L.OcclScene(self.verts.data_ptr(), self.faces.data_ptr(), vstride, fstride)
@@ -87,7 +97,7 @@ class OcclusionEngine:
         self.c_state = L.OcclState(self.elevation.data_ptr(), self.azimuth.data_ptr(), self.radius.data_ptr(),
                                    self.full_reward.data_ptr(), self.object_mass.data_ptr())
         # outputs
-        self.obs = torch.empty(N, 4, S, S, **f32)
+        self.obs = torch.empty(N, 2 if cfg.obs_planes == 2 else 4, S, S, **f32)
         self.occl = torch.empty(N, S, S, **f32)
         self.reward = torch.zeros(N, **f32)
         self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
@@ -96,6 +106,7 @@ class OcclusionEngine:
         self.n_covered = torch.zeros(N, self.n_obj, dtype=torch.int32, device=dev)
         self.n_visible = torch.zeros(N, self.n_obj, dtype=torch.int32, device=dev)
         self.status = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.status_or = torch.zeros(1, dtype=torch.int32, device=dev)  # running OR of all status words (device side)
         self.grad_action = torch.zeros(N, 2, **f32)
         self.debug = debug_outputs
         if debug_outputs:
@@ -126,6 +137,7 @@ class OcclusionEngine:
         if len(self._out_cache) > 16:
             self._out_cache.pop(next(iter(self._out_cache)))
         o.obs = (self.obs if obs is None else obs).data_ptr()
+        o.status_or = self.status_or.data_ptr()
         if scratch:
             if getattr(self, "_scratch", None) is None:
                 self._scratch = dict(occl=torch.empty_like(self.occl), loss=torch.empty_like(self.loss),
@@ -160,22 +172,48 @@ class OcclusionEngine:
                 dst.copy_(torch.as_tensor(src, dtype=torch.float32).to(self.device).expand_as(dst))
 
     def reset(self, radius=None, azimuth=None, elevation=None, obs: Optional[torch.Tensor] = None,
-              mask: Optional[torch.Tensor] = None):
+              mask: Optional[torch.Tensor] = None, scratch_outputs: bool = False):
         """Render half of OcclusionEnv.reset (environment.py:302-328).  ``mask`` (N,) uint8/bool on the
-        device restricts the reset (pose values included) to the flagged envs."""
+        device restricts the reset (pose values included) to the flagged envs.  ``scratch_outputs=True``
+        (auto-reset inside a step): only ``obs`` and the env state are updated, the other outputs of the
+        last transition (occlusion map, loss, counts, position, done) stay what the step wrote."""
         if mask is not None:
-            mask = mask.to(torch.uint8)
             assert mask.shape == (self.n,) and mask.is_cuda and mask.is_contiguous()
-            mb = mask.bool()
+            mask8 = mask if mask.dtype == torch.uint8 else mask.to(torch.uint8)
+            mb = mask8.view(torch.bool)
             for dst, src in ((self.radius, radius), (self.azimuth, azimuth), (self.elevation, elevation)):
-                if src is not None:
+                if src is None:
+                    continue
+                if isinstance(src, (int, float)):
+                    dst.masked_fill_(mb, float(src))  # one launch, no host->device copy
+                else:
                     v = torch.as_tensor(src, dtype=torch.float32).to(self.device).expand_as(dst)
                     dst.copy_(torch.where(mb, v, dst))
+            mask = mask8
         else:
             self.set_pose(radius, azimuth, elevation)
         with torch.cuda.device(self.device):
             L.check(self.lib.occl_reset(ctypes.byref(self.c), self.n, _ptr(mask), self.c_scene, self.c_state, self.c_ws,
-                                        self.outputs(False, obs), self._stream()), "occl_reset")
+                                        self.outputs(False, obs, scratch_outputs), self._stream()), "occl_reset")
+
+    def set_env_scenes(self, env_ids, scenes):
+        """Swap the meshes of some envs (per-env scenes only): the ``new_scene`` half of ``OcclusionEnv.reset``
+        (``environment.py:292-299``).  Topology sizes (V, F, object ranges) must match the engine's."""
+        if self.c_scene.verts_env_stride == 0:
+            raise L.OcclError("set_env_scenes needs an engine built with per_env_scenes")
+        env_ids = [int(i) for i in env_ids]
+        if not env_ids:
+            return
+        sc0 = self.scene
+        for sc in scenes:
+            if sc.verts.shape != sc0.verts.shape or sc.faces.shape != sc0.faces.shape or \
+                    not np.array_equal(sc.obj_face_start, sc0.obj_face_start):
+                raise L.OcclError("per-env scenes must share V, F and the object face ranges")
+        idx = torch.as_tensor(env_ids, dtype=torch.long, device=self.device)
+        v = torch.from_numpy(np.stack([np.ascontiguousarray(sc.verts, np.float32) for sc in scenes])).to(self.device)
+        f = torch.from_numpy(np.stack([np.ascontiguousarray(sc.faces, np.int32) for sc in scenes])).to(self.device)
+        self.verts.index_copy_(0, idx, v)
+        self.faces.index_copy_(0, idx, f)
 
     def step(self, action: torch.Tensor, with_grad: bool = False, obs: Optional[torch.Tensor] = None):
         """OcclusionEnv.step (environment.py:352-396) for all envs. action: (N,2) f32 on device."""
@@ -206,7 +244,6 @@ class OcclusionEngine:
         st = self._stream()
         out = self.outputs(with_grad)
         with torch.cuda.device(self.device):
-            self.status.zero_()
             L.check(lib.occl_pose_step(c, n, _ptr(action), self.c_state, cam, st), "occl_pose_step")
             L.check(lib.occl_project(c, n, cam, self.c_scene, vproj, vtan, _ptr(self.status), st), "occl_project")
             if raster_events is not None:
@@ -222,14 +259,15 @@ class OcclusionEngine:
         return self.workspace[:n].view(torch.float32).view(self.n, L.OCCL_CAM_STRIDE).clone()
 
     def check_status(self, raise_on=L.ST_ZCLIP | L.ST_HITCAP | L.ST_OVFCAP) -> int:
-        """Host-syncing check of the per-env status words; raises on conditions the kernels flag
-        instead of computing (gradient through faces cut at z_clip, selection buffers exceeded)."""
-        # bitwise OR over the envs: every flag is a single bit, so the max of each masked word will do
-        bits = (L.ST_ZCLIP, L.ST_KOVERFLOW, L.ST_HITCAP, L.ST_OVFCAP, L.ST_CLIPPED)
-        masked = torch.stack([torch.bitwise_and(self.status, b).max() for b in bits])  # one device->host copy
-        val = sum(int(v) for v in masked.tolist())
+        """Host-syncing check of the status flags raised since the last check: ONE device word (the kernels keep a
+        running OR of the per-env status words, ``OcclOutputs.status_or``), read and cleared here.  Raises on
+        conditions the kernels flag instead of computing (selection buffers exceeded).  Per-env detail stays in
+        ``self.status`` (flags of the last transition)."""
+        val = int(self.status_or.item())  # one 4-byte device->host copy
+        if val:
+            self.status_or.zero_()
         if val & raise_on:
-            raise L.OcclError(f"env status flags set: {val & raise_on:#x} (1 = the differentiable step met a face cut at z_clip = "
-                              "znear/2: no gradient flows through cut faces, 4 = more candidate faces on one pixel than the "
-                              "top-K selection buffer holds)")
+            raise L.OcclError(f"env status flags set: {val & raise_on:#x} (1 = gradient requested through a face cut at "
+                              "z_clip = znear/2 by a build without that path, 4 = more candidate faces on one pixel than "
+                              "the top-K selection buffer holds)")
         return val

@@ -188,7 +188,10 @@ def procedural_scene(seed: int, n_obj: int = 3, subdiv: int = 5) -> SceneMesh:
     object 2 offset ``(x2, 0, 1)``, object 3 offset ``(-x2, 0, 2)``, ``x2 ~ N(0,1)``."""
     rng = np.random.default_rng(seed + 7919)
     x2 = float(rng.normal())
-    offs = [(0.0, 0.0, 0.0), (x2, 0.0, 1.0), (-x2, 0.0, 2.0)][:n_obj]
+    if not 1 <= n_obj <= 4:
+        raise ValueError("procedural_scene: n_obj must be 1..4 (OCCL_MAX_OBJ)")
+    # a fourth object (not in the reference's layout) goes behind the others on the axis
+    offs = [(0.0, 0.0, 0.0), (x2, 0.0, 1.0), (-x2, 0.0, 2.0), (0.5 * x2, 0.0, -1.5)][:n_obj]
     objs = []
     for i, o in enumerate(offs):
         v, f = procedural_object(seed * 3 + i, subdiv)
