@@ -72,6 +72,10 @@
 #define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
 #endif
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
+#ifndef ROUND_FACES_FWD
+#define ROUND_FACES_FWD 256   // faces per round of the tile rasteriser's main phase (one per thread)
+#endif
+#define ROUND_FACES_GRAD 128  // ... of the differentiable kernel (its records also carry 48 B of vertex tangents)
 #ifndef BIG_FACE_PX
 #define BIG_FACE_PX 256       // faces covering more tile pixels than this are rasterised by the whole CTA (64..256 measured equal, 512 3 % slower)
 #endif
@@ -305,6 +309,7 @@ struct RasterParams {
   int* tile_idx;              // [N][n_tiles][tidx_cap] live-list indices of the faces that touch a tile
   int tidx_cap;
   const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
+  const int* clip_list;       // [1 + chunk] number of envs with faces cut at z_clip, then their (chunk-local) ids
   // outputs
   float* obs;
   int obs_planes;  // 4: R, G, B, depth planes (reference layout) ; 2: grey, depth (compact transport layout)
@@ -720,6 +725,7 @@ struct SetupParams {
   int* tile_cnt;        // [N][n_tiles] their number (may exceed tidx_cap: the raster kernel then scans the whole live list)
   int tidx_cap;
   float2* shade;        // [N][F] (ambient + diffuse, specular) of the live faces
+  int* clip_list;       // [1 + N] count, then ids, of the envs in which a face was cut at z_clip (zeroed before the launch)
   const float* verts;
   long long verts_stride;
   const float* cam;
@@ -733,7 +739,7 @@ template <bool BIN>
 __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
-  __shared__ int s_base;
+  __shared__ int s_base, s_cut;
   __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
   __shared__ int s_tcnt[BIN ? 32 * TILE_MASK_WORDS : 1];  // faces binned per tile (images of up to 256 tiles)
   const int env = blockIdx.x;
@@ -744,7 +750,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
   if (BIN)
     for (int i = tid; i < 32 * TILE_MASK_WORDS; i += SETUP_THREADS) s_tcnt[i] = 0;
   if (tid < TILE_MASK_WORDS) s_tmask[tid] = 0u;
-  if (tid == 0) s_base = 0;
+  if (tid == 0) { s_base = 0; s_cut = 0; }
   __syncthreads();
   const float4* __restrict__ vp = p.vproj + (size_t)env * p.V;
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
@@ -767,6 +773,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       if (straddles) {
         // cut at z = z_clip: the record keeps the uncut vertices, its pixel ranges are those of the cut polygon
         atomicOr(p.status + env, p.grad ? (OCCL_ST_ZCLIP | OCCL_ST_CLIPPED) : OCCL_ST_CLIPPED);  // no gradient through cut faces
+        s_cut = 1;
         SubTris st;
         clip_subtris(va, vb, vc, p.z_clip, p.cull, &st);
         live = false;
@@ -846,6 +853,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
     }
   }
   __syncthreads();
+  if (tid == 0 && s_cut) p.clip_list[1 + atomicAdd(p.clip_list, 1)] = env;  // raster_clip_kernel works through this list
   if (tid == 0) p.n_live[env] = s_base;
   if (tid < TILE_MASK_WORDS) p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = s_tmask[tid];
   if (BIN)
@@ -1050,146 +1058,146 @@ __device__ __noinline__ void clip_phase(const uint4* __restrict__ geo, const uin
   }
 }
 
-// Rare path of the pixel loop (depth queue full, or the pair went through the reference-order routine): kept out
-// of line so that the loop body stays small (L0 I-cache is ~6 KB).
-__device__ __noinline__ void hard_update_cold(unsigned long long* hard, const uint32_t* rec, int pix, float px, float py,
+// Round record of a face (tile-local, shared memory): the HOT part is what one (pixel, face) pair of the fast path
+// reads -- four 16-byte loads -- the COLD part (depths and `area`) is only needed for the exact depth of inside hits
+// and by the reference-order routine.
+//   hot  q0: x0 y0 x1 y1
+//        q1: x2 y2 | packed face index, object, flags (REC_*) | hard pixel range, tile-local, 8 bits each: x0 x1 y0 y1
+//        q2: RN(1/l2) of the edges v0v1, v0v2, v1v2 | soft box: x0 (bits 0..7), y0 (8..15), width (16..31)
+//        q3: l2 of the three edges | 1 / width
+//   cold z0 z1 z2 area
+struct RoundBuf {
+  uint4* hot;      // [R][4]
+  float4* cold;    // [R]
+  float4* tan;     // [R][3] screen-space tangents of the three vertices (GRAD)
+  int* pref;       // [R + 1] exclusive prefix sums of the faces' pixel counts
+};
+
+__device__ __forceinline__ void round_geo(const RoundBuf& rb, int f, FaceGeo* g) {
+  const uint4 a0 = rb.hot[f * 4 + 0], a1 = rb.hot[f * 4 + 1];
+  const float4 cz = rb.cold[f];
+  g->x0 = __uint_as_float(a0.x); g->y0 = __uint_as_float(a0.y); g->x1 = __uint_as_float(a0.z); g->y1 = __uint_as_float(a0.w);
+  g->x2 = __uint_as_float(a1.x); g->y2 = __uint_as_float(a1.y);
+  g->z0 = cz.x; g->z1 = cz.y; g->z2 = cz.z; g->area = cz.w;
+}
+
+// Rare paths of the pair loop, out of line so that the loop body stays small (the L0 I-cache is ~6 KB):
+// the reference-order evaluation of a pair whose guards failed ...
+__device__ __noinline__ PairResult eval_pair_round(const RoundBuf rb, int f, float px, float py) {
+  FaceGeo g;
+  round_geo(rb, f, &g);
+  return eval_pair(g, px, py);
+}
+// ... and the inline exact depth (depth queue full, or the barycentrics are already there)
+__device__ __noinline__ void hard_update_cold(unsigned long long* hard, const RoundBuf rb, int f, int pix, float px, float py,
                                               float b0, float b1, float b2, bool have_bary) {
   FaceGeo g;
-  load_geo(rec, &g);
+  round_geo(rb, f, &g);
   if (!have_bary) bary_persp(g, px, py, &b0, &b1, &b2);
   const float pz = b0 * g.z0 + b1 * g.z1 + b2 * g.z2;
   if (!(pz < 0.f)) {
     const unsigned long long key =
-        ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(rec[10] & REC_FIDX_MASK);
+        ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(rb.hot[f * 4 + 1].z & REC_FIDX_MASK);
     atomicMin(hard + pix, key);
   }
 }
 
-// One face against the pixels of its (tile-clipped) blur box; `nlanes` threads stride over them
-// (GROUP_LANES lanes of a warp for a small face -- the other groups of the warp work on other faces in
-// the same instruction stream -- or the whole CTA for a big face).  `active` = this group has a face.
-// DEFER: inside hits are queued for a dense exact-depth pass instead of being resolved in the
-// divergent loop.
-template <bool GRAD, bool DEFER>
-__device__ OCCL_RFP_INLINE void raster_face_pixels(const RasterParams& p, const TileSmem& sm, const int tile_w,
-                                                   const int tpx, const uint32_t* __restrict__ rec, int slot_id,
-                                                   int env, int lane, int nlanes, bool active) {
-  // Only what the fast path needs lives in registers across the pixel loop; the rare paths (reference-order
-  // evaluation, inline depth) reload the record from shared memory.
-  const float x0 = __uint_as_float(rec[0]), y0 = __uint_as_float(rec[1]);
-  const float x1 = __uint_as_float(rec[3]), y1 = __uint_as_float(rec[4]);
-  const float x2 = __uint_as_float(rec[6]), y2 = __uint_as_float(rec[7]);
-  const uint32_t w10 = rec[10];
+// One (pixel, face) pair: pixel `i` (row-major) of the tile-clipped blur box of round face `f`.
+template <bool GRAD>
+__device__ __forceinline__ void raster_pair(const RasterParams& p, const TileSmem& sm, const RoundBuf& rb, const int tile_w,
+                                            const int tpx, const int f, const int i) {
+  const uint4 a0 = rb.hot[f * 4 + 0], a1 = rb.hot[f * 4 + 1], a2 = rb.hot[f * 4 + 2], a3 = rb.hot[f * 4 + 3];
+  const float x0 = __uint_as_float(a0.x), y0 = __uint_as_float(a0.y), x1 = __uint_as_float(a0.z), y1 = __uint_as_float(a0.w);
+  const float x2 = __uint_as_float(a1.x), y2 = __uint_as_float(a1.y);
+  const uint32_t w10 = a1.z, sbw = a2.w;
+  const int w = (int)(sbw >> 16);
+  const int ry = (int)(((float)i + 0.5f) * __uint_as_float(a3.w));
+  const int lx = (int)(sbw & 0xffu) + (i - ry * w), ly = (int)((sbw >> 8) & 0xffu) + ry;
+  const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
   const bool fast_face = (w10 & REC_FAST) != 0u && !p.exact_only;
-  const uint32_t sb = rec[15];
-  const int lx0 = sb & 0xff, ly0 = (sb >> 16) & 0xff;
-  const int w = (int)((sb >> 8) & 0xff) - lx0 + 1, h = (int)((sb >> 24) & 0xff) - ly0 + 1;
-  const int n = active ? w * h : 0;
-  const float inv_w = __fdividef(1.0f, (float)w);
-  // per-face uniforms of the fast path
-  const float bx01 = x1 - x0, by01 = y1 - y0;
-  const float bx02 = x2 - x0, by02 = y2 - y0;
-  const float bx12 = x2 - x1, by12 = y2 - y1;
-  const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
-  const float y01 = __uint_as_float(rec[12]), y02 = __uint_as_float(rec[13]), y12 = __uint_as_float(rec[14]);  // RN(1/l2)
-  float4 ta, tb, tc;
-  if (GRAD) {
-    const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
-    const int* __restrict__ fc = p.faces + (size_t)env * p.faces_stride + 3 * (size_t)(w10 & REC_FIDX_MASK);
-    ta = __ldg(vt + __ldg(fc + 0));
-    tb = __ldg(vt + __ldg(fc + 1));
-    tc = __ldg(vt + __ldg(fc + 2));
+  bool inside, have_bary = false;
+  float dist, tt, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  int edge;
+  bool need_exact = !fast_face;
+  if (fast_face) {
+    const float bx01 = x1 - x0, by01 = y1 - y0, bx02 = x2 - x0, by02 = y2 - y0, bx12 = x2 - x1, by12 = y2 - y1;
+    const float y01 = __uint_as_float(a2.x), y02 = __uint_as_float(a2.y), y12 = __uint_as_float(a2.z);  // RN(1/l2)
+    const float l01 = __uint_as_float(a3.x), l02 = __uint_as_float(a3.y), l12 = __uint_as_float(a3.z);
+    const float dx0 = px - x0, dy0 = py - y0, dx1 = px - x1, dy1 = py - y1, dx2 = px - x2, dy2 = py - y2;
+    // edge functions in the reference's rounding (separate multiply / subtract: this TU has -fmad=false)
+    const float e0 = dx1 * by12 - dy1 * bx12;
+    const float e1 = dy2 * bx02 - dx2 * by02;
+    const float e2 = dx0 * by01 - dy0 * bx01;
+    const float ae0 = fabsf(e0), ae1 = fabsf(e1), ae2 = fabsf(e2);
+    const float emax = fmaxf(fmaxf(ae0, ae1), ae2), emin = fminf(fminf(ae0, ae1), ae2);
+    // sign(b_i) == sign(e_i) when no quotient can underflow (face guards + this spread guard)
+    const bool sign_ok = emax >= 9.313226e-10f /*2^-30*/ && emin >= 9.313226e-10f * emax;
+    inside = e0 > 0.f && e1 > 0.f && e2 > 0.f;
+    // squared distances to the three edges in the reference's operation order (bit-identical to
+    // seg_dist for non-degenerate edges, which the FAST flag guarantees): sigmoid(-d/sigma) has slope
+    // 1/sigma = 1e4, so even a 1-ulp change of a projected point would move alpha by > 1e-5 relative
+    const float n01 = bx01 * dx0 + by01 * dy0, n02 = bx02 * dx0 + by02 * dy0, n12 = bx12 * dx1 + by12 * dy1;
+    const float nmin = fminf(fminf(fabsf(n01), fabsf(n02)), fabsf(n12));
+    const float nmax = fmaxf(fmaxf(fabsf(n01), fabsf(n02)), fabsf(n12));
+    const bool div_ok = nmin >= 8.271806e-25f /*2^-80*/ && nmax <= 1024.f;  // div_rn_hoisted's domain
+    const float t01 = fminf(fmaxf(div_rn_hoisted(n01, l01, y01), 0.0f), 1.0f);
+    const float t02 = fminf(fmaxf(div_rn_hoisted(n02, l02, y02), 0.0f), 1.0f);
+    const float t12 = fminf(fmaxf(div_rn_hoisted(n12, l12, y12), 0.0f), 1.0f);
+    const float ux01 = px - (x0 + t01 * bx01), uy01 = py - (y0 + t01 * by01);
+    const float ux02 = px - (x0 + t02 * bx02), uy02 = py - (y0 + t02 * by02);
+    const float ux12 = px - (x1 + t12 * bx12), uy12 = py - (y1 + t12 * by12);
+    const float d01 = ux01 * ux01 + uy01 * uy01;
+    const float d02 = ux02 * ux02 + uy02 * uy02;
+    const float d12 = ux12 * ux12 + uy12 * uy12;
+    dist = fminf(fminf(d01, d02), d12);
+    if (d01 <= d02 && d01 <= d12) { edge = 0; tt = t01; }
+    else if (d02 <= d12) { edge = 1; tt = t02; }
+    else { edge = 2; tt = t12; }
+    // shortcuts taken: inside test by signs (no six divisions), divisions by hoisted reciprocal
+    need_exact = !(sign_ok && div_ok);
   }
-  unsigned long long* soft = sm.soft + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx;
-  for (int i = lane; i < n; i += nlanes) {
-    const int ry = (int)(((float)i + 0.5f) * inv_w);
-    const int rx = i - ry * w;
-    const int lx = lx0 + rx, ly = ly0 + ry;
-    const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
-    bool inside, have_bary = false;
-    float dist, tt, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-    int edge;
-    bool need_exact = !fast_face;
-    if (fast_face) {
-      const float dx0 = px - x0, dy0 = py - y0, dx1 = px - x1, dy1 = py - y1, dx2 = px - x2, dy2 = py - y2;
-      // edge functions in the reference's rounding (separate multiply / subtract: this TU has -fmad=false)
-      const float e0 = dx1 * by12 - dy1 * bx12;
-      const float e1 = dy2 * bx02 - dx2 * by02;
-      const float e2 = dx0 * by01 - dy0 * bx01;
-      const float a0 = fabsf(e0), a1 = fabsf(e1), a2 = fabsf(e2);
-      const float emax = fmaxf(fmaxf(a0, a1), a2), emin = fminf(fminf(a0, a1), a2);
-      // sign(b_i) == sign(e_i) when no quotient can underflow (face guards + this spread guard)
-      const bool sign_ok = emax >= 9.313226e-10f /*2^-30*/ && emin >= 9.313226e-10f * emax;
-      inside = e0 > 0.f && e1 > 0.f && e2 > 0.f;
-      // squared distances to the three edges in the reference's operation order (bit-identical to
-      // seg_dist for non-degenerate edges, which the FAST flag guarantees): sigmoid(-d/sigma) has slope
-      // 1/sigma = 1e4, so even a 1-ulp change of a projected point would move alpha by > 1e-5 relative
-      const float n01 = bx01 * dx0 + by01 * dy0, n02 = bx02 * dx0 + by02 * dy0, n12 = bx12 * dx1 + by12 * dy1;
-      const float nmin = fminf(fminf(fabsf(n01), fabsf(n02)), fabsf(n12));
-      const float nmax = fmaxf(fmaxf(fabsf(n01), fabsf(n02)), fabsf(n12));
-      const bool div_ok = nmin >= 8.271806e-25f /*2^-80*/ && nmax <= 1024.f;  // div_rn_hoisted's domain
-      const float t01 = fminf(fmaxf(div_rn_hoisted(n01, l01, y01), 0.0f), 1.0f);
-      const float t02 = fminf(fmaxf(div_rn_hoisted(n02, l02, y02), 0.0f), 1.0f);
-      const float t12 = fminf(fmaxf(div_rn_hoisted(n12, l12, y12), 0.0f), 1.0f);
-      const float ux01 = px - (x0 + t01 * bx01), uy01 = py - (y0 + t01 * by01);
-      const float ux02 = px - (x0 + t02 * bx02), uy02 = py - (y0 + t02 * by02);
-      const float ux12 = px - (x1 + t12 * bx12), uy12 = py - (y1 + t12 * by12);
-      const float d01 = ux01 * ux01 + uy01 * uy01;
-      const float d02 = ux02 * ux02 + uy02 * uy02;
-      const float d12 = ux12 * ux12 + uy12 * uy12;
-      dist = fminf(fminf(d01, d02), d12);
-      if (d01 <= d02 && d01 <= d12) { edge = 0; tt = t01; }
-      else if (d02 <= d12) { edge = 1; tt = t02; }
-      else { edge = 2; tt = t12; }
-      // shortcuts taken: inside test by signs (no six divisions), divisions by hoisted reciprocal
-      need_exact = !(sign_ok && div_ok);
-    }
-    if (need_exact) {
-      FaceGeo g;
-      load_geo(rec, &g);
-      const PairResult r = eval_pair(g, px, py);
-      inside = r.inside; dist = r.dist; tt = r.t; edge = r.edge;
-      b0 = r.b0; b1 = r.b1; b2 = r.b2;
-      have_bary = true;
-    }
-    if (!inside && dist >= p.blur) continue;
-    const int pix = ly * tile_w + lx;
-    const float sd = inside ? -dist : dist;
-    bool hard_ok = false;
-    if (inside) {
-      const uint32_t hb = rec[11];
-      hard_ok = lx >= (int)(hb & 0xff) && lx <= (int)((hb >> 8) & 0xff) && ly >= (int)((hb >> 16) & 0xff) &&
-                ly <= (int)((hb >> 24) & 0xff);
-    }
-    soft_accumulate(soft + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
-    if (hard_ok) {
-      bool queued = false;
-      if (DEFER && !have_bary) {
-        const int d = atomicAdd(sm.defer_n, 1);
-        if (d < WDEFER_CAP) {
-          sm.defer[d] = (uint32_t)pix | ((uint32_t)slot_id << 16);
-          queued = true;
-        }
+  if (need_exact) {
+    const PairResult r = eval_pair_round(rb, f, px, py);
+    inside = r.inside; dist = r.dist; tt = r.t; edge = r.edge;
+    b0 = r.b0; b1 = r.b1; b2 = r.b2;
+    have_bary = true;
+  }
+  if (!inside && dist >= p.blur) return;
+  const int pix = ly * tile_w + lx;
+  const float sd = inside ? -dist : dist;
+  bool hard_ok = false;
+  if (inside) {
+    const uint32_t hb = a1.w;
+    hard_ok = lx >= (int)(hb & 0xff) && lx <= (int)((hb >> 8) & 0xff) && ly >= (int)((hb >> 16) & 0xff) &&
+              ly <= (int)((hb >> 24) & 0xff);
+  }
+  const int obj = (int)((w10 >> REC_OBJ_SHIFT) & 3u);
+  soft_accumulate(sm.soft + (size_t)obj * tpx + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
+  if (hard_ok) {
+    bool queued = false;
+    if (!have_bary) {
+      const int d = atomicAdd(sm.defer_n, 1);
+      if (d < WDEFER_CAP) {
+        sm.defer[d] = (uint32_t)pix | ((uint32_t)f << 16);
+        queued = true;
       }
-      if (!queued) hard_update_cold(sm.hard, rec, pix, px, py, b0, b1, b2, have_bary);
     }
-    if (GRAD) {
-      // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
-      float ax, ay, bx, by;
-      float4 da, db;
-      if (edge == 0) { ax = x0; ay = y0; bx = x1; by = y1; da = ta; db = tb; }
-      else if (edge == 1) { ax = x0; ay = y0; bx = x2; by = y2; da = ta; db = tc; }
-      else { ax = x1; ay = y1; bx = x2; by = y2; da = tb; db = tc; }
-      const float qx = ax + tt * (bx - ax), qy = ay + tt * (by - ay);
-      const float sgn = inside ? -1.f : 1.f;
-      const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
-      const float wa = 1.f - tt, wb = tt;
-      const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
-      const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
-      const float prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
-      const float k = prob * p.inv_sigma;
-      grad_accumulate(sm.gacc + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx + pix, k * dsd_el, k * dsd_az);
-    }
+    if (!queued) hard_update_cold(sm.hard, rb, f, pix, px, py, b0, b1, b2, have_bary);
+  }
+  if (GRAD) {
+    // d signed_dist / d theta through the nearest edge, vertices move, pixel fixed
+    const int ia = edge == 2 ? 1 : 0, ib = edge == 0 ? 1 : 2;
+    const float4 da = rb.tan[f * 3 + ia], db = rb.tan[f * 3 + ib];
+    const float ax = ia ? x1 : x0, ay = ia ? y1 : y0, bx = ib == 1 ? x1 : x2, by = ib == 1 ? y1 : y2;
+    const float qx = ax + tt * (bx - ax), qy = ay + tt * (by - ay);
+    const float sgn = inside ? -1.f : 1.f;
+    const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+    const float wa = 1.f - tt, wb = tt;
+    const float dsd_el = gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y);
+    const float dsd_az = gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w);
+    const float prob = rcp_approx(1.0f + ex2_approx(sd * p.inv_sigma_log2e));  // sigmoid(-sd/sigma), ~2 ulp
+    const float k = prob * p.inv_sigma;
+    grad_accumulate(sm.gacc + (size_t)obj * tpx + pix, k * dsd_el, k * dsd_az);
   }
 }
 
@@ -1703,8 +1711,8 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   const int tpx = tile_w * tile_h;
   const int S = p.S;
 
-  __shared__ int s_chunk, s_big_n, s_tidx_n;
-  __shared__ int s_wdef_n[OCCL_WARPS];
+  __shared__ int s_tidx_n;
+  __shared__ int s_wdef_n[OCCL_WARPS], s_wsum[OCCL_WARPS];
   __shared__ double s_red[OCCL_WARPS][4];
   __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
 
@@ -1776,16 +1784,11 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     for (int i = tid; i < tpx * p.n_obj; i += OCCL_THREADS) sm.gacc[i] = 0ull;
   for (int i = tid; i < tile_w; i += OCCL_THREADS) sm.ndc_x[i] = pix_to_ndc(S - 1 - (tx0 + i), S);
   for (int i = tid; i < tile_h; i += OCCL_THREADS) sm.ndc_y[i] = pix_to_ndc(S - 1 - (ty0 + i), S);
-  // faces of this tile as binned by the setup kernel (else: every live face of the env is range-tested here)
-  // (compiled only into the dense-scene tile and the generic kernel: the 32x32 kernel of config 2 lost 3 % to the
-  //  mere presence of this branch in its scan loop)
-  constexpr bool BIN = !(TW == OCCL_TILE_W && TH == OCCL_TILE_H);
-  const int n_bin = BIN && p.tile_cnt ? __ldg(p.tile_cnt + (size_t)env * n_tiles + tile) : -1;
-  // (only for well-filled tiles: a chunk of the binned list is 32 faces of THIS tile, and with fewer than four chunks
-  //  per warp the dynamic balancing gets too coarse -- config 2 lost 3.5 % -- while a chunk of the whole live list
-  //  carries only a few faces of the tile)
-  const bool binned = BIN && n_bin >= 128 * OCCL_WARPS && n_bin <= p.tidx_cap;
-  if (tid == 0) { s_chunk = 0; s_big_n = 0; s_tidx_n = binned ? n_bin : 0; }
+  // faces of this tile as binned by the setup kernel; if there is no binning (images of more than 256 tiles) or the
+  // tile's list overflowed its capacity, every live face of the env is range-tested here instead
+  const int n_bin = p.tile_cnt ? __ldg(p.tile_cnt + (size_t)env * n_tiles + tile) : -1;
+  const bool binned = n_bin >= 0 && n_bin <= p.tidx_cap;
+  if (tid == 0) s_tidx_n = binned ? n_bin : 0;
   if (tid < OCCL_WARPS) s_wdef_n[tid] = 0;
   __syncthreads();
 
@@ -1797,40 +1800,47 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   const int tx1 = tx0 + tile_w - 1, ty1 = ty0 + tile_h - 1;
   int* __restrict__ tidx = p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap;
 
-  // ---- every warp on its own: scan a 32-face slice of the env's live list, stage the faces whose blur box
-  // ---- overlaps the tile (ballot compaction) in the warp's buffer, scatter them, repeat.  No CTA barrier.
+  // ---- main phase: rounds of up to R faces of the tile ----------------------------------------------------
+  // A round (a) loads R face records into shared memory, one per thread, and block-scans their pixel counts
+  // (pixels of the tile-clipped blur box), then (b) deals the round's (pixel, face) PAIRS evenly to the warps: warp w
+  // takes the pairs [T w / 8, T (w + 1) / 8) of the round's T, lane l the pairs l, l + 32, ... of that range -- every
+  // lane has work in every trip whatever the sizes of the faces (a one-pixel sliver and a box side covering the tile
+  // are the same to this loop), the warps finish together, consecutive lanes sit on consecutive pixels of (mostly)
+  // the same face, so the record loads are broadcasts and the accumulator atomics hit consecutive banks.
+  // A pair finds its face by advancing through the prefix sums (a binary search once per round and lane).
   {
-    uint32_t* wbuf = sm.list + warp * (WBUF_RECS * REC_WORDS);
+    constexpr int R = GRAD ? ROUND_FACES_GRAD : ROUND_FACES_FWD;
+    static_assert(R <= OCCL_THREADS && R <= 256, "one face per thread; slot ids are 8 bits in the depth queue");
+    static_assert((size_t)R * (64 + 16 + (GRAD ? 48 : 0)) + 4 * (R + 1) <= (size_t)4 * OCCL_WARPS * WBUF_RECS * REC_WORDS,
+                  "round buffers must fit the aliased region");
+    RoundBuf rb;
+    rb.hot = (uint4*)sm.list;
+    rb.cold = (float4*)(rb.hot + R * 4);
+    rb.tan = (float4*)(rb.cold + R);
+    rb.pref = (int*)(rb.tan + (GRAD ? R * 3 : 0));
     sm.defer = sm.defer + warp * WDEFER_CAP;
     sm.defer_n = &s_wdef_n[warp];
-    int cnt = 0;  // records pending in wbuf (warp-uniform)
-    // Work unit = a "chunk" of 16 face pairs taken with stride n_chunks through the env's live list (mesh
-    // order is spatially coherent, so a strided chunk samples the whole mesh and every chunk carries about
-    // the same share of this tile's faces; a pair = 32 B of ranges = one sector).  Warps grab chunks
-    // dynamically.
     const int n_src = binned ? n_bin : n_live;
-    const int n_chunks = (n_src + 31) >> 5;
-    for (;;) {
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&s_chunk, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      const bool scanning = c < n_chunks;
-      if (scanning) {
-        int k = 2 * (c + n_chunks * (lane >> 1)) + (lane & 1);  // position in the source list
-        const bool valid = k < n_src;
-        if (binned && valid) k = tidx[k];
+    for (int base = 0; base < n_src; base += R) {
+      // (a) one candidate per thread
+      int npx = 0;
+      {
+        const int c = base + tid;
         bool keep = false;
-        int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+        int k = 0;
         uint4 rg = make_uint4(0, 0, 0, 0);
-        if (valid) {
+        int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+        if (tid < R && c < n_src) {
+          k = binned ? __ldg(tidx + c) : c;
           rg = __ldg(rng + k);
           cx0 = max((int)(rg.x & 0xffffu), tx0);  cx1 = min((int)(rg.x >> 16), tx1);
           cy0 = max((int)(rg.y & 0xffffu), ty0);  cy1 = min((int)(rg.y >> 16), ty1);
           keep = cx0 <= cx1 && cy0 <= cy1;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        // without binning: remember which live faces touch this tile (the K-overflow passes rescan only those)
         if (!binned) {
+          // no list from the setup kernel: remember which live faces touch this tile (the K-overflow and clip passes
+          // rescan only those)
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
           int tbase = 0;
           if (lane == 0 && bal) tbase = atomicAdd(&s_tidx_n, __popc(bal));
           tbase = __shfl_sync(0xffffffffu, tbase, 0);
@@ -1838,135 +1848,93 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
           if (keep && tpos < p.tidx_cap) tidx[tpos] = k;
         }
         if (keep) {
-          const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
           const uint4* __restrict__ src = geo + (size_t)k * 4;
-          uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+          const uint4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
           int hx0 = max((int)(rg.z & 0xffffu), tx0) - tx0, hx1 = min((int)((rg.z >> 16) & 0x7fffu), tx1) - tx0;
           int hy0 = max((int)(rg.w & 0xffffu), ty0) - ty0, hy1 = min((int)((rg.w >> 16) & 0x3fffu), ty1) - ty0;
           if (hx0 > hx1 || hy0 > hy1) { hx0 = 255; hx1 = 0; hy0 = 255; hy1 = 0; }
-          q2.w = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
-          q3.w = (uint32_t)(cx0 - tx0) | ((uint32_t)(cx1 - tx0) << 8) | ((uint32_t)(cy0 - ty0) << 16) |
-                 ((uint32_t)(cy1 - ty0) << 24);
-          if (CLIPF && (rg.z & RNG_CLIP)) q3.w = 1u;  // cut face (z-clip): empty box here, rasterised by the clip phase
-          uint4* dst = (uint4*)(wbuf + slot * REC_WORDS);
-          dst[0] = q0; dst[1] = q1; dst[2] = q2; dst[3] = q3;
-        }
-        cnt += __popc(bal);
-      }
-      __syncwarp();
-      // process batches of (up to) 32 staged faces, taken from the END of the buffer so that the
-      // leftover stays in place; the whole remainder once the scan is over
-      while (cnt >= BATCH_MIN || (!scanning && cnt > 0)) {
-        const int batch = min(cnt, 32);
-        const int first = cnt - batch;
-        // lane l < batch looks at face first + l: its pixel count (0 for a big face, which is set aside)
-        int npx_l = 0, npx_raw = 0;
-        bool big_l = false;
-        if (lane < batch) {
-          const uint32_t sb = wbuf[(first + lane) * REC_WORDS + 15];
-          npx_raw = (int)(((sb >> 8) & 0xff) - (sb & 0xff) + 1) * (int)(((sb >> 24) & 0xff) - ((sb >> 16) & 0xff) + 1);
-          big_l = npx_raw > BIG_FACE_PX;
-          npx_l = big_l ? 0 : npx_raw;
-        }
-        // faces with many pixels are set aside for the whole CTA (after the barrier-free phase); if the
-        // shared list is full they stay in the batch (the lane allocation gives them most of the warp)
-        unsigned bigmask = __ballot_sync(0xffffffffu, big_l);
-        while (bigmask) {
-          const int bl = __ffs(bigmask) - 1;
-          const int jj = first + bl;
-          bigmask &= bigmask - 1;
-          int bslot = 0;
-          if (lane == 0) bslot = atomicAdd(&s_big_n, 1);
-          bslot = __shfl_sync(0xffffffffu, bslot, 0);
-          if (bslot < BIG_CAP) {
-            if (lane < REC_WORDS) sm.big[bslot * REC_WORDS + lane] = wbuf[jj * REC_WORDS + lane];
-          } else if (lane == bl) {
-            npx_l = npx_raw;
+          const uint32_t hb = (uint32_t)hx0 | ((uint32_t)hx1 << 8) | ((uint32_t)hy0 << 16) | ((uint32_t)hy1 << 24);
+          const int w = cx1 - cx0 + 1;
+          const uint32_t sbw = (uint32_t)(cx0 - tx0) | ((uint32_t)(cy0 - ty0) << 8) | ((uint32_t)w << 16);
+          const float x0 = __uint_as_float(q0.x), y0 = __uint_as_float(q0.y), x1 = __uint_as_float(q0.w), y1 = __uint_as_float(q1.x);
+          const float x2 = __uint_as_float(q1.z), y2 = __uint_as_float(q1.w);
+          const float bx01 = x1 - x0, by01 = y1 - y0, bx02 = x2 - x0, by02 = y2 - y0, bx12 = x2 - x1, by12 = y2 - y1;
+          const float l01 = bx01 * bx01 + by01 * by01, l02 = bx02 * bx02 + by02 * by02, l12 = bx12 * bx12 + by12 * by12;
+          rb.hot[tid * 4 + 0] = make_uint4(q0.x, q0.y, q0.w, q1.x);
+          rb.hot[tid * 4 + 1] = make_uint4(q1.z, q1.w, q2.z, hb);
+          rb.hot[tid * 4 + 2] = make_uint4(q3.x, q3.y, q3.z, sbw);
+          rb.hot[tid * 4 + 3] = make_uint4(__float_as_uint(l01), __float_as_uint(l02), __float_as_uint(l12),
+                                           __float_as_uint(__fdividef(1.0f, (float)w)));
+          rb.cold[tid] = make_float4(__uint_as_float(q0.z), __uint_as_float(q1.y), __uint_as_float(q2.x), __uint_as_float(q2.y));
+          if (GRAD) {
+            const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+            const int* __restrict__ fc = faces + 3 * (size_t)(q2.z & REC_FIDX_MASK);
+            rb.tan[tid * 3 + 0] = __ldg(vt + __ldg(fc + 0));
+            rb.tan[tid * 3 + 1] = __ldg(vt + __ldg(fc + 1));
+            rb.tan[tid * 3 + 2] = __ldg(vt + __ldg(fc + 2));
           }
+          npx = w * (cy1 - cy0 + 1);
+          if (CLIPF && (rg.z & RNG_CLIP)) npx = 0;  // cut face (z-clip): rasterised by the clip phase
         }
-        // One pass = 4 consecutive faces of the batch sharing the warp; the 32 lanes are dealt to them in
-        // proportion to their pixel counts, so that all faces of a pass need (almost) the same number of loop
-        // trips.  The lane boundaries of ALL passes are computed at once: lane l works them out for face l
-        // (segmented scans over groups of 4 lanes), a pass then only fetches three of them.
-        int cstart, ptotal;
-        {
-          const int g = lane & 3;
-          int v = npx_l;
-          int t = __shfl_up_sync(0xffffffffu, v, 1);
-          if (g >= 1) v += t;
-          t = __shfl_up_sync(0xffffffffu, v, 2);
-          if (g >= 2) v += t;
-          const int total = __shfl_sync(0xffffffffu, v, lane | 3);
-          ptotal = total;
-          cstart = total > 0 ? __float2int_rn((float)(v - npx_l) * __fdividef(32.0f, (float)total)) : 0;
-          const int has = npx_l > 0 ? 1 : 0;
-          // every face with pixels gets at least one lane: forward, then backward within the group
+      }
+      // exclusive block scan of the pixel counts
+      int incl = npx;
 #pragma unroll
-          for (int sidx = 1; sidx <= 3; ++sidx) {
-            const int pc = __shfl_up_sync(0xffffffffu, cstart, 1), ph = __shfl_up_sync(0xffffffffu, has, 1);
-            if (g == sidx) cstart = max(cstart, pc + ph);
-          }
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
 #pragma unroll
-          for (int sidx = 3; sidx >= 1; --sidx) {
-            const int nc = __shfl_down_sync(0xffffffffu, cstart, 1);
-            if (g == sidx) cstart = min(cstart, (g == 3 ? 32 : nc) - has);
+      for (int w = 0; w < OCCL_WARPS; ++w) {
+        const int v = s_wsum[w];
+        if (w < warp) woff += v;
+        total += v;
+      }
+      if (tid < R) rb.pref[tid] = woff + incl - npx;
+      if (tid == R - 1 || (R == OCCL_THREADS && tid == OCCL_THREADS - 1)) rb.pref[R] = total;
+      __syncthreads();
+      // (b) this warp's share of the round's pairs
+      const int w_begin = (int)(((long long)total * warp) / OCCL_WARPS), w_end = (int)(((long long)total * (warp + 1)) / OCCL_WARPS);
+      int j = w_begin + lane;
+      int f = 0;
+      {
+        int lo = 0, hi = R;  // largest f with pref[f] <= j (empty faces share their successor's prefix: skipped)
+#pragma unroll 1
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (rb.pref[mid] <= j) lo = mid; else hi = mid;
+        }
+        f = lo;
+      }
+      int fstart = rb.pref[f], fend = rb.pref[f + 1];
+#pragma unroll 1
+      for (int jb = w_begin; jb < w_end; jb += 32, j += 32) {
+        if (j < w_end) {
+          while (j >= fend) { ++f; fstart = fend; fend = rb.pref[f + 1]; }
+          raster_pair<GRAD>(p, sm, rb, tile_w, tpx, f, j - fstart);
+        }
+        __syncwarp();
+        // dense exact-depth pass over this warp's queued inside hits, before the queue can overflow
+        const int nd = *(volatile int*)sm.defer_n;
+        if (nd > WDEFER_CAP - 32 || jb + 32 >= w_end) {
+          for (int q = lane; q < min(nd, WDEFER_CAP); q += 32) {
+            const uint32_t d = sm.defer[q];
+            const int pix = (int)(d & 0xffffu), fq = (int)(d >> 16);
+            FaceGeo g;
+            round_geo(rb, fq, &g);
+            const int ly = pix / tile_w, lx = pix - ly * tile_w;
+            hard_update(sm, g, (int)(rb.hot[fq * 4 + 1].z & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
           }
-          if (g == 0) cstart = 0;
+          __syncwarp();
+          if (lane == 0) *sm.defer_n = 0;
+          __syncwarp();
         }
-        for (int f0 = 0; f0 < batch; f0 += 4) {
-          const int c1 = __shfl_sync(0xffffffffu, cstart, f0 + 1), c2 = __shfl_sync(0xffffffffu, cstart, f0 + 2),
-                    c3 = __shfl_sync(0xffffffffu, cstart, f0 + 3);
-          if (__shfl_sync(0xffffffffu, ptotal, f0) == 0) continue;  // nothing but set-aside faces in this pass
-          const int g_mine = (lane >= c1) + (lane >= c2) + (lane >= c3);
-          const int start = g_mine == 0 ? 0 : (g_mine == 1 ? c1 : (g_mine == 2 ? c2 : c3));
-          const int end = g_mine == 0 ? c1 : (g_mine == 1 ? c2 : (g_mine == 2 ? c3 : 32));
-          const int j = first + min(f0 + g_mine, batch - 1);
-          raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, wbuf + j * REC_WORDS, j, env, lane - start, end - start,
-                                         f0 + g_mine < batch && end > start);
-        }
-        __syncwarp();
-        // dense exact-depth pass over this warp's queued inside hits
-        const int nd = min(*sm.defer_n, WDEFER_CAP);
-        for (int q = lane; q < nd; q += 32) {
-          const uint32_t d = sm.defer[q];
-          const int pix = (int)(d & 0xffffu);
-          const uint32_t* rec = wbuf + (d >> 16) * REC_WORDS;
-          FaceGeo g;
-          load_geo(rec, &g);
-          const int ly = pix / tile_w, lx = pix - ly * tile_w;
-          hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
-        }
-        __syncwarp();
-        if (lane == 0) *sm.defer_n = 0;
-        cnt = first;
-        __syncwarp();
       }
-      if (!scanning) break;
+      __syncthreads();  // the next round overwrites the records
     }
-  }
-  __syncthreads();
-  // ---- big faces: the whole CTA on one face at a time --------------------------------------------
-  {
-    const int nb = min(s_big_n, BIG_CAP);
-    for (int b = 0; b < nb; ++b) {
-      raster_face_pixels<GRAD, true>(p, sm, tile_w, tpx, sm.big + b * REC_WORDS, b, env, tid, OCCL_THREADS, true);
-      __syncwarp();
-      // this warp's queued inside hits of face b
-      const int nd = min(*sm.defer_n, WDEFER_CAP);
-      for (int q = lane; q < nd; q += 32) {
-        const uint32_t d = sm.defer[q];
-        const int pix = (int)(d & 0xffffu);
-        const uint32_t* rec = sm.big + (d >> 16) * REC_WORDS;
-        FaceGeo g;
-        load_geo(rec, &g);
-        const int ly = pix / tile_w, lx = pix - ly * tile_w;
-        hard_update(sm, g, (int)(rec[10] & REC_FIDX_MASK), pix, sm.ndc_x[lx], sm.ndc_y[ly], 0.f, 0.f, 0.f, false);
-      }
-      __syncwarp();
-      if (lane == 0) *sm.defer_n = 0;
-      __syncwarp();
-    }
-    if (nb) __syncthreads();
   }
 
   // ---- cut faces (z-clip) ------------------------------------------------------------------------
@@ -2139,16 +2107,18 @@ raster_kernel(const RasterParams p) {
   raster_tile<GRAD, TW, TH, DBG, false>(p, env, tile);
 }
 
-// One CTA per env, only for envs with cut faces (camera within z_clip = znear/2 of the geometry): the tiles in
-// turn, with the clip-capable instantiation of the tile rasteriser.  Everywhere else the CTA leaves at once.
+// Envs with cut faces (camera within z_clip = znear/2 of the geometry), which the setup kernel has listed: a fixed
+// grid of CTAs works through the (listed env, tile) items with the clip-capable instantiation of the tile rasteriser
+// (generic tile shape).  With an empty list -- every BASELINE teapot pose -- the few CTAs leave at once.  (One CTA per
+// env was the first version: a dense env then ran on 1/592 of the GPU; one CTA per (env, tile) of the whole batch the
+// second: 65 536 CTAs that only look at a flag cost 0.12 ms per config-2 step.)
 template <bool GRAD>
 __global__ void __launch_bounds__(OCCL_THREADS) raster_clip_kernel(const RasterParams p) {
-  const int env = blockIdx.x;
-  if (p.env_mask && !p.env_mask[env]) return;
-  if (!(*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED)) return;
   const int n_tiles = p.tiles_x * p.tiles_y;
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    raster_tile<GRAD, 0, 0, true, true>(p, env, tile);
+  const int n_items = __ldg(p.clip_list) * n_tiles;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int env = __ldg(p.clip_list + 1 + it / n_tiles);
+    raster_tile<GRAD, 0, 0, true, true>(p, env, it % n_tiles);
     __syncthreads();
   }
 }
@@ -2252,10 +2222,12 @@ static cudaError_t ensure_dyn_smem(size_t smem) {
 }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, clip_list, total;
   int tidx_cap;
   int n_tiles;
   int chunk;  // envs rasterised per launch: the per-face scratch (geo .. tile_cnt) is sized for this many, not for N
+  int sets;   // 1: all envs in one launch; 2: two scratch sets, the chunks alternate between them on two streams
+  size_t set_stride;  // bytes from a set-0 scratch buffer to its set-1 twin
 };
 
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
@@ -2342,7 +2314,17 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
                          sizeof(int) + sizeof(uint32_t) * TILE_MASK_WORDS;
   const size_t budget = (size_t)(c->ws_budget_mb > 0 ? c->ws_budget_mb : 2048) << 20;
   size_t chunk = budget / per_env;
-  if (chunk < 1) chunk = 1;
+  L->sets = 1;
+  if (chunk < (size_t)n) {
+    // two half-size scratch sets: chunk c + 1 is set up and rasterised (second stream) while the last, heavy tiles of
+    // chunk c finish -- a chunked batch then runs like one long launch instead of paying a tail per chunk
+    L->sets = 2;
+    chunk = budget / 2 / per_env;
+    if (chunk < 1) chunk = 1;
+    // equal chunks
+    const size_t n_chunks = ((size_t)n + chunk - 1) / chunk;
+    chunk = ((size_t)n + n_chunks - 1) / n_chunks;
+  }
   if (chunk > (size_t)n) chunk = (size_t)n;
   L->chunk = (int)chunk;
   const size_t m = chunk;
@@ -2358,8 +2340,27 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->shade = off;    off = align_up(off + sizeof(float2) * m * c->n_faces, 256);
   L->tile_idx = off; off = align_up(off + sizeof(int) * m * L->n_tiles * L->tidx_cap, 256);
   L->tile_cnt = off; off = align_up(off + sizeof(int) * m * L->n_tiles, 256);
+  L->clip_list = off; off = align_up(off + sizeof(int) * (m + 1), 256);
+  L->set_stride = off - L->geo;
+  if (L->sets == 2) off += L->set_stride;
   L->total = off;
   return 0;
+}
+
+// Two internal streams per device for the chunk pipeline (created once, never destroyed).
+static int chunk_streams(cudaStream_t out[2]) {
+  static cudaStream_t pool[64][2];
+  static bool have[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return OCCL_E_CUDA;
+  if (!have[dev]) {
+    for (int k = 0; k < 2; ++k)
+      if (cudaStreamCreateWithFlags(&pool[dev][k], cudaStreamNonBlocking) != cudaSuccess) return OCCL_E_CUDA;
+    have[dev] = true;
+  }
+  out[0] = pool[dev][0];
+  out[1] = pool[dev][1];
+  return OCCL_OK;
 }
 
 extern "C" size_t occl_workspace_bytes(const OcclConfig* cfg, int n_envs, int with_grad) {
@@ -2462,8 +2463,9 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.tile_mask = (const uint32_t*)(base + L.tile_mask);
   p.shade = (const float2*)(base + L.shade);
   p.tile_idx = (int*)(base + L.tile_idx); p.tidx_cap = L.tidx_cap;
-  // binning pays for dense scenes only (config 3 +8 %; on config 2 the extra work of the setup kernel costs 3 %)
-  const bool bin = L.n_tiles <= 32 * TILE_MASK_WORDS && (c.n_obj >= 3 || c.n_faces >= OCCL_DENSE_FACES);
+  // the setup kernel bins the live faces per tile whenever the image has at most 256 tiles (its shared-memory counters);
+  // the raster CTAs then read their own list instead of range-testing every live face of the env
+  const bool bin = L.n_tiles <= 32 * TILE_MASK_WORDS;
   p.tile_cnt = bin ? (const int*)(base + L.tile_cnt) : nullptr;
   p.light[0] = c.light[0]; p.light[1] = c.light[1]; p.light[2] = c.light[2];
   p.vproj = (const float4*)(base + L.vproj);
@@ -2498,9 +2500,33 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   const RasterParams p0 = p;
   // chunk after chunk of envs through the same per-face scratch (see ws_layout): every per-env array is entered at
   // the chunk's first env, so that the kernels index everything by the env's position inside the chunk
-  for (int e0 = 0; e0 < n; e0 += L.chunk) {
+  cudaStream_t lanes[2] = {(cudaStream_t)stream, (cudaStream_t)stream};
+  cudaEvent_t ev_fork = nullptr;
+  if (L.sets == 2) {
+    if (chunk_streams(lanes) != OCCL_OK) return cuda_fail(cudaGetLastError(), "chunk streams");
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "event");
+    CK(cudaEventRecord(ev_fork, (cudaStream_t)stream), "fork");
+    CK(cudaStreamWaitEvent(lanes[0], ev_fork, 0), "fork");
+    CK(cudaStreamWaitEvent(lanes[1], ev_fork, 0), "fork");
+    CK(cudaEventDestroy(ev_fork), "event");
+  }
+  int ci = 0;
+  for (int e0 = 0; e0 < n; e0 += L.chunk, ++ci) {
     const int m = n - e0 < L.chunk ? n - e0 : L.chunk;
     const size_t e = (size_t)e0;
+    cudaStream_t lane = lanes[ci & 1];
+    {
+      unsigned char* sb = base + (size_t)(L.sets == 2 ? (ci & 1) : 0) * L.set_stride;
+      p.geo = (uint4*)(sb + L.geo); p.rng = (uint4*)(sb + L.rng); p.n_live = (int*)(sb + L.n_live);
+      p.tile_mask = (const uint32_t*)(sb + L.tile_mask);
+      p.shade = (const float2*)(sb + L.shade);
+      p.tile_idx = (int*)(sb + L.tile_idx);
+      p.tile_cnt = bin ? (const int*)(sb + L.tile_cnt) : nullptr;
+      sp.geo = p.geo; sp.rng = p.rng; sp.n_live = p.n_live; sp.tile_mask = (uint32_t*)(sb + L.tile_mask);
+      sp.shade = (float2*)(sb + L.shade); sp.tile_idx = p.tile_idx; sp.tile_cnt = bin ? (int*)(sb + L.tile_cnt) : nullptr;
+      sp.clip_list = (int*)(sb + L.clip_list); p.clip_list = sp.clip_list;
+      CK(cudaMemsetAsync(sp.clip_list, 0, sizeof(int), lane), "memset clip list");
+    }
     p.vproj = p0.vproj + e * c.n_verts;
     p.vtan = p0.vtan ? p0.vtan + e * c.n_verts : nullptr;
     p.verts = p0.verts + e * (size_t)p0.verts_stride;
@@ -2518,13 +2544,14 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     sp.vproj = p.vproj; sp.faces = p.faces; sp.verts = p.verts; sp.cam = p.cam; sp.status = p.status;
     sp.env_mask = p.env_mask;
     const long long blocks = (long long)m * L.n_tiles;
-    if (bin) face_setup_kernel<true><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
-    else face_setup_kernel<false><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, (cudaStream_t)stream>>>(sp);
+    const unsigned clip_grid = (unsigned)(blocks < 2 * 148 ? blocks : 2 * 148);
+    if (bin) face_setup_kernel<true><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, lane>>>(sp);
+    else face_setup_kernel<false><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, lane>>>(sp);
     CK(cudaGetLastError(), "face_setup_kernel");
 #define OCCL_LAUNCH_RASTER(G, W, H, D)                                                                                   \
   do {                                                                                                                   \
     CK((ensure_dyn_smem<raster_kernel<G, W, H, D>>(smem)), "smem attr");                                                  \
-    raster_kernel<G, W, H, D><<<(unsigned)blocks, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);                         \
+    raster_kernel<G, W, H, D><<<(unsigned)blocks, OCCL_THREADS, smem, lane>>>(p);                                         \
   } while (0)
 #define OCCL_LAUNCH_RASTER_G(G)                                                                 \
   do {                                                                                          \
@@ -2542,12 +2569,21 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile
     if (grad) {
       CK(ensure_dyn_smem<raster_clip_kernel<true>>(smem), "smem attr");
-      raster_clip_kernel<true><<<(unsigned)m, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+      raster_clip_kernel<true><<<clip_grid, OCCL_THREADS, smem, lane>>>(p);
     } else {
       CK(ensure_dyn_smem<raster_clip_kernel<false>>(smem), "smem attr");
-      raster_clip_kernel<false><<<(unsigned)m, OCCL_THREADS, smem, (cudaStream_t)stream>>>(p);
+      raster_clip_kernel<false><<<clip_grid, OCCL_THREADS, smem, lane>>>(p);
     }
     CK(cudaGetLastError(), "raster_kernel");
+  }
+  if (L.sets == 2) {
+    for (int k = 0; k < 2; ++k) {  // join: the caller's stream continues when both lanes are done
+      cudaEvent_t ev_join;
+      CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "event");
+      CK(cudaEventRecord(ev_join, lanes[k]), "join");
+      CK(cudaStreamWaitEvent((cudaStream_t)stream, ev_join, 0), "join");
+      CK(cudaEventDestroy(ev_join), "event");
+    }
   }
   return OCCL_OK;
 }

@@ -116,7 +116,8 @@ def test_chunked_workspace_equals_unchunked(cuda_lib):
     assert b.workspace.numel() < a.workspace.numel() // 4
     for name in ("obs", "occl", "alphas", "pix_to_face", "nhits", "n_covered", "n_visible", "reward", "done", "loss", "status"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
-    torch.testing.assert_close(a.grad_action, b.grad_action, rtol=1e-5, atol=1e-7)
+    # the tangent sums are float adds in arrival order: equal up to that noise
+    torch.testing.assert_close(a.grad_action, b.grad_action, rtol=1e-4, atol=1e-6)
 
 
 def test_auto_reset_keeps_terminal_info(oracle, cuda_lib):

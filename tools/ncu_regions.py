@@ -8,7 +8,8 @@ import sys
 rep = sys.argv[1]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-lines = open('/root/repo/occlusionenv_b200/csrc/occl_b200.cu').read().split('\n')
+import os
+lines = open(os.environ.get('OCCL_SRC', '/root/repo/occlusionenv_b200/csrc/occl_b200.cu')).read().split('\n')
 
 
 def find(pat):
