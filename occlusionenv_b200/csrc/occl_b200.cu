@@ -450,8 +450,21 @@ __device__ __forceinline__ float soft_prob(float signed_dist, float sigma) {
 
 // Exact pixel range of an NDC interval [lo, hi]: pixels whose centre c satisfies !(c>hi) && !(c<lo).
 // Pixel centres DEcrease with the index; tab[i] = pix_to_ndc(S-1-i, S) (exact reference values).
+// For a power-of-two S every centre is the exact value (S - 1 - 2 i) / S, so that the two comparisons reduce to
+// i >= (S - 1 - hi S) / 2 and i <= (S - 1 - lo S) / 2, evaluated in double (hi S and the difference are exact there):
+// no table look-ups, no correction loops.
 __device__ __forceinline__ void ndc_range_to_pixels(const float* __restrict__ tab, float lo, float hi,
                                                     int S, int* i0, int* i1) {
+  if ((S & (S - 1)) == 0) {
+    const double dS = (double)S;
+    double a = ceil(((dS - 1.0) - (double)hi * dS) * 0.5);
+    double b = floor(((dS - 1.0) - (double)lo * dS) * 0.5);
+    a = fmin(fmax(a, 0.0), dS);          // NaN bounds select the whole range, as the general path does
+    b = fmin(fmax(b, -1.0), dS - 1.0);
+    *i0 = (hi == hi) ? (int)a : 0;
+    *i1 = (lo == lo) ? (int)b : S - 1;
+    return;
+  }
   const float fS = (float)S;
   float e0 = ceilf(((1.0f - hi) * fS - 1.0f) * 0.5f);   // estimates, exact up to rounding: the loops
   float e1 = floorf(((1.0f - lo) * fS - 1.0f) * 0.5f);  // below settle the last pixel either way
@@ -512,20 +525,22 @@ __device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, in
     ctr[k] = ((v0[k] + q1) + q2) / 3.0f;
   }
   float n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+  // (the normalisations multiply by one reciprocal instead of dividing three times, the 64th power is six squarings:
+  //  colours are on the tolerance side of the path, compared at 1e-5 relative)
   float nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
-  nn = nn > 1e-6f ? nn : 1e-6f;
-  n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+  nn = 1.0f / (nn > 1e-6f ? nn : 1e-6f);
+  n[0] = n[0] * nn; n[1] = n[1] * nn; n[2] = n[2] * nn;
   nn = sqrtf((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
-  nn = nn > 1e-6f ? nn : 1e-6f;
-  n[0] = n[0] / nn; n[1] = n[1] / nn; n[2] = n[2] / nn;
+  nn = 1.0f / (nn > 1e-6f ? nn : 1e-6f);
+  n[0] = n[0] * nn; n[1] = n[1] * nn; n[2] = n[2] * nn;
   float dir[3] = {light[0] - ctr[0], light[1] - ctr[1], light[2] - ctr[2]};
   float view[3] = {camx - ctr[0], camy - ctr[1], camz - ctr[2]};
   float dn = sqrtf((dir[0] * dir[0] + dir[1] * dir[1]) + dir[2] * dir[2]);
-  dn = dn > 1e-6f ? dn : 1e-6f;
-  dir[0] = dir[0] / dn; dir[1] = dir[1] / dn; dir[2] = dir[2] / dn;
+  dn = 1.0f / (dn > 1e-6f ? dn : 1e-6f);
+  dir[0] = dir[0] * dn; dir[1] = dir[1] * dn; dir[2] = dir[2] * dn;
   float vn = sqrtf((view[0] * view[0] + view[1] * view[1]) + view[2] * view[2]);
-  vn = vn > 1e-6f ? vn : 1e-6f;
-  view[0] = view[0] / vn; view[1] = view[1] / vn; view[2] = view[2] / vn;
+  vn = 1.0f / (vn > 1e-6f ? vn : 1e-6f);
+  view[0] = view[0] * vn; view[1] = view[1] * vn; view[2] = view[2] * vn;
   const float cosang = (n[0] * dir[0] + n[1] * dir[1]) + n[2] * dir[2];
   const float diffuse = 0.3f * (cosang > 0.f ? cosang : 0.f);
   const float r0 = -dir[0] + 2.0f * (cosang * n[0]);
@@ -533,7 +548,8 @@ __device__ __forceinline__ float2 face_lighting(const float* __restrict__ wv, in
   const float r2 = -dir[2] + 2.0f * (cosang * n[2]);
   float al = (view[0] * r0 + view[1] * r1) + view[2] * r2;
   al = (al > 0.f ? al : 0.f) * (cosang > 0.f ? 1.0f : 0.0f);
-  return make_float2(0.5f + diffuse, 0.2f * powf(al, 64.0f));
+  al = al * al; al = al * al; al = al * al; al = al * al; al = al * al; al = al * al;
+  return make_float2(0.5f + diffuse, 0.2f * al);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -756,10 +772,31 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
   uint4* __restrict__ geo = p.geo + (size_t)env * p.F * 4;
   uint4* __restrict__ rng = p.rng + (size_t)env * p.F;
-  // Warps take 32-face chunks in turn and reserve list slots with one atomic per chunk: the list is in
-  // mesh order up to the interleaving of concurrently finishing warps (nothing depends on its order).
-  for (int base = warp * 32; base < p.F; base += SETUP_THREADS) {
-    const int f = base + lane;
+  // Warps take 64-face chunks in turn.  Pass A (cheap): the culls -- about half the faces of a closed mesh are back
+  // faces -- and a ballot compaction of the survivors into the warp's queue; pass B (ranges, record, lighting, binning):
+  // dense over the queue, so that its lanes are busy whatever the cull rate.  List slots are reserved with one atomic
+  // per pass: the list is in mesh order up to the interleaving of concurrently finishing warps (nothing depends on
+  // its order).
+  __shared__ int s_wl[SETUP_WARPS][64];
+  for (int base = warp * 64; base < p.F; base += SETUP_WARPS * 64) {
+    int nl = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int fa = base + half * 32 + lane;
+      bool keep = false;
+      if (fa < p.F) {
+        const int i0 = __ldg(faces + 3 * fa + 0), i1 = __ldg(faces + 3 * fa + 1), i2 = __ldg(faces + 3 * fa + 2);
+        bool straddles = false;
+        FaceGeo ga;
+        keep = face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, p.z_clip, &ga, &straddles) || straddles;
+      }
+      const unsigned kb = __ballot_sync(0xffffffffu, keep);
+      if (keep) s_wl[warp][nl + __popc(kb & ((1u << lane) - 1u))] = fa;
+      nl += __popc(kb);
+    }
+    __syncwarp();
+   for (int q0 = 0; q0 < nl; q0 += 32) {
+    const int f = q0 + lane < nl ? s_wl[warp][q0 + lane] : p.F;
     bool live = false, clipf = false;
     FaceGeo g;
     int sx0 = 0, sx1 = -1, sy0 = 0, sy1 = -1, hx0 = 0, hx1 = -1, hy0 = 0, hy1 = -1;
@@ -851,6 +888,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
                              (uint32_t)hx0 | ((uint32_t)hx1 << 16) | (clipf ? RNG_CLIP : 0u),
                              (uint32_t)hy0 | ((uint32_t)hy1 << 16) | (obj << 30));
     }
+   }
+   __syncwarp();  // the queue is rewritten by the next chunk
   }
   __syncthreads();
   if (tid == 0 && s_cut) p.clip_list[1 + atomicAdd(p.clip_list, 1)] = env;  // raster_clip_kernel works through this list

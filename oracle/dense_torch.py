@@ -80,10 +80,53 @@ def pixel_centers(S, dtype):
     return c
 
 
+Z_CLIP = 0.5  # MeshRasterizer: z_clip_value = znear / 2 for perspective cameras
+
+
+def clip_faces(fv, z_clip=Z_CLIP):
+    """pytorch3d ``clip_faces`` (renderer/mesh/clip.py, the frustum MeshRasterizer builds) on face vertices
+    ``fv`` (F,3,3) = (x_ndc, y_ndc, z_view), DIFFERENTIABLY: the cut vertices p4 / p5 are functions of the face's own
+    vertices (interpolation in view space, re-projection), so autograd carries the gradient of a hit on a cut
+    triangle back to the uncut vertices -- what pytorch3d's autograd does through its torch ops.  Same cases and vertex
+    orders as ``oracle/oracle.py::clip_faces``.  Returns (clipped fv (Fc,3,3), neighbour index (Fc,) long, -1 = none)."""
+    behind = fv[:, :, 2].detach() < z_clip
+    n = behind.sum(dim=1)
+    out, nb = [], []
+
+    def cut(p1, q):
+        w = (p1[2] - z_clip) / (p1[2] - q[2])
+        x = ((p1[0] * p1[2]) * (1.0 - w) + (q[0] * q[2]) * w) / z_clip
+        y = ((p1[1] * p1[2]) * (1.0 - w) + (q[1] * q[2]) * w) / z_clip
+        return torch.stack([x, y, torch.as_tensor(z_clip, dtype=fv.dtype)])
+
+    keep = (n == 0).nonzero()[:, 0]
+    out.append(fv[keep])
+    nb.append(torch.full((len(keep),), -1, dtype=torch.long))
+    count = len(keep)
+    for f in ((n == 1) | (n == 2)).nonzero()[:, 0].tolist():
+        v, b = fv[f], behind[f]
+        i = int(torch.argmax(b.to(torch.int8))) if int(n[f]) == 1 else int(torch.argmax((~b).to(torch.int8)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        p1, p2, p3 = v[i], v[j], v[k]
+        p4, p5 = cut(p1, p2), cut(p1, p3)
+        if int(n[f]) == 1:
+            out.append(torch.stack([torch.stack([p4, p2, p5]), torch.stack([p5, p2, p3])]))
+            nb.append(torch.tensor([count + 1, count], dtype=torch.long))
+            count += 2
+        else:
+            out.append(torch.stack([p1, p4, p5])[None])
+            nb.append(torch.tensor([-1], dtype=torch.long))
+            count += 1
+    return torch.cat(out, dim=0), torch.cat(nb, dim=0)
+
+
 def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
     """Soft silhouette alpha for the pixel rows ``rows`` (1-D long tensor): (len(rows), S)."""
     dtype = vproj.dtype
     fv = vproj[faces]  # (F,3,3)
+    nb = None
+    if bool((fv[:, :, 2].detach() < Z_CLIP).any()):
+        fv, nb = clip_faces(fv)
     x0, y0, z0 = fv[:, 0, 0], fv[:, 0, 1], fv[:, 0, 2]
     x1, y1, z1 = fv[:, 1, 0], fv[:, 1, 1], fv[:, 1, 2]
     x2, y2, z2 = fv[:, 2, 0], fv[:, 2, 1], fv[:, 2, 2]
@@ -124,6 +167,19 @@ def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
     dist = torch.minimum(torch.minimum(_seg(PX, PY, x0, y0, x1, y1), _seg(PX, PY, x0, y0, x2, y2)),
                          _seg(PX, PY, x1, y1, x2, y2))
     hit = in_box & (pz >= 0) & (inside | (dist < blur))
+    if nb is not None:
+        # clipped_faces_neighbor_idx: of the two triangles of a cut quadrilateral hitting one pixel only the one with
+        # the smaller distance is kept (the first on ties), as the face loop of the reference does
+        pos = torch.full((nb.numel(),), -1, dtype=torch.long)
+        pos[idx] = torch.arange(idx.numel())
+        mate = torch.where(nb[idx] >= 0, pos[nb[idx].clamp_min(0)], torch.full_like(idx, -1))
+        has = mate >= 0
+        if bool(has.any()):
+            m = mate.clamp_min(0)
+            d_self, d_mate = dist.detach(), dist.detach()[:, m]
+            first = (torch.arange(idx.numel()) < m)[None, :]
+            lose = hit[:, m] & has[None, :] & torch.where(first, d_mate < d_self, d_mate <= d_self)
+            hit = hit & ~lose
     nh = hit.sum(dim=1)
     if int(nh.max()) > K:
         # keep the K nearest by (pz, face index): stable sort on pz keeps the lower index first on ties

@@ -22,16 +22,14 @@ def find(pat):
 marks = [
     ("exact helpers (eval_pair, bary, seg)", "__device__ __forceinline__ float seg_dist", "// raw SFU approximations"),
     ("div_rn_hoisted / sfu", "// raw SFU approximations", "// clipped-barycentric depth"),
-    ("soft_accumulate / hard_update", "__device__ __forceinline__ void soft_accumulate", "// One face against the pixels"),
-    ("raster_face_pixels", "// One face against the pixels", "// Tangent terms of one soft hit"),
-    ("tile prologue (mask, init)", "__device__ __forceinline__ void raster_tile(", "// ---- every warp on its own"),
+    ("soft_accumulate / soft_term", "// soft accumulator of a (pixel, object) slot", "__device__ __forceinline__ unsigned long long pack2f"),
+    ("raster_pair (pair evaluation)", "// Round record of a face", "// Tangent terms of one soft hit"),
+    ("tile prologue (mask, init)", "__device__ __forceinline__ void raster_tile(", "// ---- main phase: rounds of up to R faces"),
     ("cut faces (z-clip)", "// z-clip: pytorch3d renderer/mesh/clip.py::clip_faces", "// kernel 2: per-env face setup"),
-    ("scan + stage", "// ---- every warp on its own", "// process batches of (up to) 32 staged faces"),
-    ("batch sort + pass dispatch", "// process batches of (up to) 32 staged faces", "// dense exact-depth pass over this warp"),
-    ("deferred depth pass", "// dense exact-depth pass over this warp", "// ---- big faces: the whole CTA"),
-    ("big faces (CTA)", "// ---- big faces: the whole CTA", "// ---- pixels with more than K hits: keep the K nearest"),
+    ("round fill + scan", "// ---- main phase: rounds of up to R faces", "// (b) this warp's share of the round's pairs"),
+    ("pair loop (advance, dispatch, depth queue)", "// (b) this warp's share of the round's pairs", "// ---- cut faces (z-clip) ---"),
     ("top-K overflow (pre-scan)", "// ---- pixels with more than K hits: keep the K nearest", "// ---- epilogue: blend, shade"),
-    ("top-K overflow: hit-list rounds", "// K-overflow resolution of one tile.", "// ---- pixels with more hits than a round holds"),
+    ("top-K overflow: warp-per-slot + rounds", "// K-overflow resolution of one tile.", "// ---- pixels with more hits than a round holds"),
     ("top-K overflow: one-pixel fallback", "// ---- pixels with more hits than a round holds", "// TW, TH: compile-time tile shape"),
     ("hit_tangent", "// Tangent terms of one soft hit", "__device__ __forceinline__ double warp_sum"),
     ("epilogue", "// ---- epilogue: blend, shade", "// kernel 6: per-env finalisation"),
