@@ -38,8 +38,8 @@ extern "C" {
 #define OCCL_E_SMEM (-3)     /* tile does not fit in shared memory */
 
 /* per-env status bits */
-#define OCCL_ST_ZCLIP 1u       /* the differentiable step met a face that straddles z_view = z_clip: faces are cut there as
-                                  pytorch3d's clip_faces does, but no gradient flows through cut faces (not implemented) */
+#define OCCL_ST_ZCLIP 1u       /* reserved: was "gradient requested through a face cut at z_clip" before the cut
+                                  triangles carried tangents; never set */
 #define OCCL_ST_CLIPPED 16u    /* informational: some face was cut at z_clip (clip_faces cases 3/4) */
 #define OCCL_ST_KOVERFLOW 2u   /* some pixel had more than faces_per_pixel hits (handled: nearest-K rule applied) */
 #define OCCL_ST_HITCAP 4u      /* a pixel had more hits than the top-K selection buffer: alpha of that pixel is wrong */
@@ -130,6 +130,12 @@ int occl_abi_version(void);
 
 /* Human-readable text of the last CUDA error seen by this library on the calling thread. */
 const char* occl_last_cuda_error(void);
+
+/* Let kernels launched on the CURRENT device store through pointers into `peer_device`'s memory (NVLink / NVSwitch
+ * peer access): needed once per process before OcclOutputs.obs may point into another GPU's gather buffer -- the
+ * fused "render + deliver to the learner" path of occlusionenv_b200/dist.py (the cross-GPU torch.stack of
+ * SubProcVecEnv.py:219).  Idempotent. */
+int occl_enable_peer_access(int peer_device);
 
 /* Self-test of the rasteriser's division primitive: counts, over n_samples pseudo-random operand
  * pairs of its guarded domain, the results that are not bit-identical to IEEE `a / b`.

@@ -627,6 +627,8 @@ __device__ __noinline__ void clip_subtris(const float4 a, const float4 b, const 
 // if strictly closer (clipped_faces_neighbor_idx rule of the reference's face loop).
 struct ClipPixel {
   bool soft_hit, soft_inside, hard_hit;
+  int soft_which, soft_edge;  // cut triangle of the soft hit, its nearest edge (0: v0v1, 1: v0v2, 2: v1v2) ...
+  float soft_t;               // ... and the clamped parameter on it (for the gradient)
   float soft_dist, soft_pz;   // squared distance (unsigned), clipped-barycentric depth
   float hard_pz;              // perspective-correct depth of the nearest... of the chosen triangle
   int hard_which;
@@ -636,6 +638,7 @@ struct ClipPixel {
 __device__ __noinline__ void eval_clip_pixel(const SubTris* st, const float px, const float py, const float blur,
                                              const float bbox_r, ClipPixel* o) {
   o->soft_hit = false; o->hard_hit = false; o->soft_inside = false;
+  o->soft_which = 0; o->soft_edge = 0; o->soft_t = 0.f;
   o->soft_dist = 0.f; o->soft_pz = 0.f; o->hard_pz = 0.f; o->hard_which = 0; o->hb0 = o->hb1 = o->hb2 = 0.f;
   float hard_dist = 0.f;
   for (int t = 0; t < st->n; ++t) {
@@ -649,6 +652,7 @@ __device__ __noinline__ void eval_clip_pixel(const SubTris* st, const float px, 
       const float pz = pz_clipped(g, r.b0, r.b1, r.b2);
       if (!(pz < 0.f) && (!o->soft_hit || r.dist < o->soft_dist)) {
         o->soft_hit = true; o->soft_inside = r.inside; o->soft_dist = r.dist; o->soft_pz = pz;
+        o->soft_which = t; o->soft_edge = r.edge; o->soft_t = r.t;
       }
     }
     if (r.inside && !(px > xhi || px < xlo || py > yhi || py < ylo)) {
@@ -674,6 +678,89 @@ __device__ __noinline__ bool clip_soft_eval(const uint4* __restrict__ rec, const
   eval_clip_pixel(&st, px, py, blur, bbox_r, &cp);
   *inside = cp.soft_inside; *dist = cp.soft_dist; *pz = cp.soft_pz;
   return cp.soft_hit;
+}
+
+// Screen-space tangents d(x_ndc, y_ndc)/d(el, az) of the vertices of the cut triangles of face `fidx` (same cases and
+// vertex orders as clip_subtris).  An uncut vertex carries the tangent the projection kernel wrote; a plane
+// intersection p4 = cut(p1, q), x4 = ((x1 z1)(1 - w) + (xq zq) w) / z_clip with w = (z1 - z_clip) / (z1 - zq), moves
+// with x, y AND z of both end points -- pytorch3d gets the same derivative by autograd through clip_faces.
+// d z_view / d theta is recomputed from the world vertex and the camera tangent blocks (cut faces are rare).
+struct SubTrisTan {
+  float4 t[2][3];
+};
+
+__device__ __noinline__ void clip_subtris_tan(const RasterParams& p, const int env, const int fidx, const float4 a,
+                                              const float4 b, const float4 c, const float zc, SubTrisTan* out) {
+  const int* __restrict__ fc = p.faces + (size_t)env * p.faces_stride + 3 * (size_t)fidx;
+  const int vi[3] = {__ldg(fc + 0), __ldg(fc + 1), __ldg(fc + 2)};
+  const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
+  const float* __restrict__ cam = p.cam + (size_t)env * OCCL_CAM_STRIDE;
+  const float4 pv[3] = {a, b, c};
+  float4 tv[3];
+  float dz[3][2];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    tv[k] = __ldg(vt + vi[k]);
+    const float* __restrict__ w = p.verts + (size_t)env * p.verts_stride + 3 * (size_t)vi[k];
+    const float x = __ldg(w + 0), y = __ldg(w + 1), z = __ldg(w + 2);
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const float* __restrict__ dc = cam + 16 * (d + 1);
+      dz[k][d] = x * __ldg(dc + 2) + y * __ldg(dc + 5) + z * __ldg(dc + 8) + __ldg(dc + 11);
+    }
+  }
+  const bool c0 = a.z < zc, c1 = b.z < zc, c2 = c.z < zc;
+  const int n = (int)c0 + (int)c1 + (int)c2;
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out->t[t][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n == 0 || n == 3) return;
+  const int i = n == 1 ? (c0 ? 0 : (c1 ? 1 : 2)) : (!c0 ? 0 : (!c1 ? 1 : 2));  // the isolated vertex
+  const int j = (i + 1) % 3, k = (i + 2) % 3;
+  auto cut_tan = [&](const int q) {
+    const float4 p1 = pv[i], pq = pv[q];
+    const float den = p1.z - pq.z;
+    const float w = (p1.z - zc) / den;
+    float r[4];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const float dz1 = dz[i][d], dzq = dz[q][d];
+      const float dw = (dz1 * den - (p1.z - zc) * (dz1 - dzq)) / (den * den);
+      const float dx1 = d == 0 ? tv[i].x : tv[i].z, dy1 = d == 0 ? tv[i].y : tv[i].w;
+      const float dxq = d == 0 ? tv[q].x : tv[q].z, dyq = d == 0 ? tv[q].y : tv[q].w;
+      r[2 * d + 0] = ((dx1 * p1.z + p1.x * dz1) * (1.0f - w) - (p1.x * p1.z) * dw + (dxq * pq.z + pq.x * dzq) * w + (pq.x * pq.z) * dw) / zc;
+      r[2 * d + 1] = ((dy1 * p1.z + p1.y * dz1) * (1.0f - w) - (p1.y * p1.z) * dw + (dyq * pq.z + pq.y * dzq) * w + (pq.y * pq.z) * dw) / zc;
+    }
+    return make_float4(r[0], r[1], r[2], r[3]);
+  };
+  const float4 t4 = cut_tan(j), t5 = cut_tan(k);
+  if (n == 1) {  // t1 = (p4, p2, p5), t2 = (p5, p2, p3)
+    out->t[0][0] = t4; out->t[0][1] = tv[j]; out->t[0][2] = t5;
+    out->t[1][0] = t5; out->t[1][1] = tv[j]; out->t[1][2] = tv[k];
+  } else {       // (p1, p4, p5)
+    out->t[0][0] = tv[i]; out->t[0][1] = t4; out->t[0][2] = t5;
+  }
+}
+
+// p_k / sigma * d(signed dist)/d(el, az) of a soft hit on a cut face (SURVEY A.7 on the cut triangle)
+__device__ __noinline__ void clip_hit_tangent(const RasterParams& p, const SubTris* st, const SubTrisTan* tt,
+                                              const ClipPixel* cp, const float px, const float py, float* g0, float* g1) {
+  const FaceGeo& g = st->g[cp->soft_which];
+  const float4* tq = tt->t[cp->soft_which];
+  float ax, ay, bx, by;
+  float4 da, db;
+  if (cp->soft_edge == 0) { ax = g.x0; ay = g.y0; bx = g.x1; by = g.y1; da = tq[0]; db = tq[1]; }
+  else if (cp->soft_edge == 1) { ax = g.x0; ay = g.y0; bx = g.x2; by = g.y2; da = tq[0]; db = tq[2]; }
+  else { ax = g.x1; ay = g.y1; bx = g.x2; by = g.y2; da = tq[1]; db = tq[2]; }
+  const float t = cp->soft_t;
+  const float qx = ax + t * (bx - ax), qy = ay + t * (by - ay);
+  const float sgn = cp->soft_inside ? -1.f : 1.f;
+  const float gx = sgn * 2.f * (qx - px), gy = sgn * 2.f * (qy - py);
+  const float wa = 1.f - t, wb = t;
+  const float kk = soft_prob(cp->soft_inside ? -cp->soft_dist : cp->soft_dist, p.sigma) / p.sigma;
+  *g0 += kk * (gx * (wa * da.x + wb * db.x) + gy * (wa * da.y + wb * db.y));
+  *g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
 }
 
 // K-overflow round: hits of one cut face on the slots of the round (one lane; rare)
@@ -809,7 +896,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) face_setup_kernel(const SetupPa
       float ylo = fminf(fminf(g.y0, g.y1), g.y2), yhi = fmaxf(fmaxf(g.y0, g.y1), g.y2);
       if (straddles) {
         // cut at z = z_clip: the record keeps the uncut vertices, its pixel ranges are those of the cut polygon
-        atomicOr(p.status + env, p.grad ? (OCCL_ST_ZCLIP | OCCL_ST_CLIPPED) : OCCL_ST_CLIPPED);  // no gradient through cut faces
+        atomicOr(p.status + env, OCCL_ST_CLIPPED);
         s_cut = 1;
         SubTris st;
         clip_subtris(va, vb, vc, p.z_clip, p.cull, &st);
@@ -1040,13 +1127,17 @@ __device__ __noinline__ void raster_clip_record(const uint4* __restrict__ rec, c
                                                 const int cy1, unsigned long long* soft_all, unsigned long long* hard,
                                                 const float* ndc_x, const float* ndc_y, const int tile_w, const int tpx,
                                                 const float z_clip, const int cull, const float blur, const float bbox_r,
-                                                const float inv_sigma_log2e, const int lane) {
+                                                const float inv_sigma_log2e, const int lane, const RasterParams* gp,
+                                                const int env, unsigned long long* gacc_all) {
   const uint4 q0 = __ldg(rec + 0), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+  const float4 va = make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), 0.f);
+  const float4 vb = make_float4(__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), 0.f);
+  const float4 vc = make_float4(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), 0.f);
   SubTris st;
-  clip_subtris(make_float4(__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), 0.f),
-               make_float4(__uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y), 0.f),
-               make_float4(__uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), 0.f), z_clip, cull, &st);
+  clip_subtris(va, vb, vc, z_clip, cull, &st);
   const uint32_t w10 = q2.z;
+  SubTrisTan tt;
+  if (gp) clip_subtris_tan(*gp, env, (int)(w10 & REC_FIDX_MASK), va, vb, vc, z_clip, &tt);  // differentiable step
   unsigned long long* soft = soft_all + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx;
   const int w = cx1 - cx0 + 1, n = w * (cy1 - cy0 + 1);
   for (int i = lane; i < n; i += 32) {
@@ -1057,6 +1148,11 @@ __device__ __noinline__ void raster_clip_record(const uint4* __restrict__ rec, c
     if (cp.soft_hit) {
       const float sd = cp.soft_inside ? -cp.soft_dist : cp.soft_dist;
       soft_accumulate(soft + pix, soft_term(sd, inv_sigma_log2e), cp.hard_hit);
+      if (gp) {
+        float g0 = 0.f, g1 = 0.f;
+        clip_hit_tangent(*gp, &st, &tt, &cp, ndc_x[lx], ndc_y[ly], &g0, &g1);
+        grad_accumulate(gacc_all + (size_t)((w10 >> REC_OBJ_SHIFT) & 3u) * tpx + pix, g0, g1);
+      }
     }
     if (cp.hard_hit) {
       const unsigned low = (w10 & REC_FIDX_MASK) | KEY_CLIP | ((unsigned)cp.hard_which << 30);
@@ -1072,7 +1168,8 @@ __device__ __noinline__ void clip_phase(const uint4* __restrict__ geo, const uin
                                         const int ty0, const int tx1, const int ty1, unsigned long long* soft_all,
                                         unsigned long long* hard, const float* ndc_x, const float* ndc_y, const int tile_w,
                                         const int tpx, const float z_clip, const int cull, const float blur,
-                                        const float bbox_r, const float inv_sigma_log2e) {
+                                        const float bbox_r, const float inv_sigma_log2e, const RasterParams* gp,
+                                        const int env, unsigned long long* gacc_all) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c0 = warp * 32; c0 < n_cand; c0 += OCCL_THREADS) {
     const int ci = c0 + lane;
@@ -1092,7 +1189,7 @@ __device__ __noinline__ void clip_phase(const uint4* __restrict__ geo, const uin
       const int bx0 = __shfl_sync(0xffffffffu, cx0, bl), bx1 = __shfl_sync(0xffffffffu, cx1, bl);
       const int by0 = __shfl_sync(0xffffffffu, cy0, bl), by1 = __shfl_sync(0xffffffffu, cy1, bl);
       raster_clip_record(geo + (size_t)kb * 4, bx0 - tx0, bx1 - tx0, by0 - ty0, by1 - ty0, soft_all, hard, ndc_x, ndc_y,
-                         tile_w, tpx, z_clip, cull, blur, bbox_r, inv_sigma_log2e, lane);
+                         tile_w, tpx, z_clip, cull, blur, bbox_r, inv_sigma_log2e, lane, gp, env, gacc_all);
     }
   }
 }
@@ -1247,8 +1344,21 @@ __device__ __noinline__ void hit_tangent(const RasterParams& p, int env, int f, 
   const int* __restrict__ faces = p.faces + (size_t)env * p.faces_stride;
   const int i0 = __ldg(faces + 3 * f + 0), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
   FaceGeo g;
-  bool straddles_unused;
-  face_geo(__ldg(vp + i0), __ldg(vp + i1), __ldg(vp + i2), p.cull, 0.f, &g, &straddles_unused);
+  bool straddles = false;
+  const float4 va = __ldg(vp + i0), vb = __ldg(vp + i1), vc = __ldg(vp + i2);
+  face_geo(va, vb, vc, p.cull, p.z_clip, &g, &straddles);
+  if (straddles) {  // a face cut at z_clip: the hit is on one of its cut triangles
+    SubTris st;
+    clip_subtris(va, vb, vc, p.z_clip, p.cull, &st);
+    ClipPixel cp;
+    eval_clip_pixel(&st, px, py, p.blur, p.bbox_r, &cp);
+    if (cp.soft_hit) {
+      SubTrisTan tt;
+      clip_subtris_tan(p, env, f, va, vb, vc, p.z_clip, &tt);
+      clip_hit_tangent(p, &st, &tt, &cp, px, py, g0, g1);
+    }
+    return;
+  }
   const PairResult r = eval_pair(g, px, py);
   const float prob = soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
   const float4* __restrict__ vt = p.vtan + (size_t)env * p.V;
@@ -1986,7 +2096,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     clip_phase(p.geo + (size_t)env * p.F * 4, p.rng + (size_t)env * p.F,
                p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap, use_t ? n_t : p.n_live[env], use_t, ctx0, cty0,
                ctx0 + tile_w - 1, cty0 + tile_h - 1, csm.soft, csm.hard, csm.ndc_x, csm.ndc_y, tile_w, tile_w * tile_h, p.z_clip,
-               p.cull, p.blur, p.bbox_r, p.inv_sigma_log2e);
+               p.cull, p.blur, p.bbox_r, p.inv_sigma_log2e, GRAD ? &p : nullptr, env, csm.gacc);
     __syncthreads();
   }
 
@@ -2309,6 +2419,25 @@ extern "C" int occl_selftest_div(unsigned long long n_samples, unsigned long lon
 }
 
 extern "C" int occl_abi_version(void) { return OCCL_ABI_VERSION; }
+
+extern "C" int occl_enable_peer_access(int peer_device) {
+  int dev = 0;
+  CK(cudaGetDevice(&dev), "cudaGetDevice");
+  if (dev == peer_device) return OCCL_OK;
+  int can = 0;
+  CK(cudaDeviceCanAccessPeer(&can, dev, peer_device), "cudaDeviceCanAccessPeer");
+  if (!can) {
+    snprintf(g_last_err, sizeof(g_last_err), "device %d cannot access device %d (no NVLink / PCIe peer path)", dev, peer_device);
+    return OCCL_E_CUDA;
+  }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return OCCL_OK;
+  }
+  CK(e, "cudaDeviceEnablePeerAccess");
+  return OCCL_OK;
+}
 extern "C" const char* occl_last_cuda_error(void) { return g_last_err; }
 
 extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {

@@ -62,7 +62,12 @@ def _share_cuda_tensor(t: Optional[torch.Tensor], src: int):
     if dist.get_rank() == src:
         return t
     fn, args = box[0]
-    return fn(*args)
+    peer = fn(*args)
+    # torch maps the block in the exporting device's context of THIS process; kernels of this rank's own device need
+    # peer access to it (torch only enables that for its own copies)
+    from . import _lib as L
+    L.check(L.load().occl_enable_peer_access(int(peer.device.index)), "occl_enable_peer_access")
+    return peer
 
 
 class LearnerGather:

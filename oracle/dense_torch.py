@@ -91,7 +91,7 @@ def clip_faces(fv, z_clip=Z_CLIP):
     orders as ``oracle/oracle.py::clip_faces``.  Returns (clipped fv (Fc,3,3), neighbour index (Fc,) long, -1 = none)."""
     behind = fv[:, :, 2].detach() < z_clip
     n = behind.sum(dim=1)
-    out, nb = [], []
+    out, nb, key = [], [], []
 
     def cut(p1, q):
         w = (p1[2] - z_clip) / (p1[2] - q[2])
@@ -101,8 +101,8 @@ def clip_faces(fv, z_clip=Z_CLIP):
 
     keep = (n == 0).nonzero()[:, 0]
     out.append(fv[keep])
-    nb.append(torch.full((len(keep),), -1, dtype=torch.long))
-    count = len(keep)
+    key.append(2 * keep)
+    mates = []  # (key of a triangle, key of its neighbour)
     for f in ((n == 1) | (n == 2)).nonzero()[:, 0].tolist():
         v, b = fv[f], behind[f]
         i = int(torch.argmax(b.to(torch.int8))) if int(n[f]) == 1 else int(torch.argmax((~b).to(torch.int8)))
@@ -111,17 +111,53 @@ def clip_faces(fv, z_clip=Z_CLIP):
         p4, p5 = cut(p1, p2), cut(p1, p3)
         if int(n[f]) == 1:
             out.append(torch.stack([torch.stack([p4, p2, p5]), torch.stack([p5, p2, p3])]))
-            nb.append(torch.tensor([count + 1, count], dtype=torch.long))
-            count += 2
+            key.append(torch.tensor([2 * f, 2 * f + 1]))
+            mates += [(2 * f, 2 * f + 1), (2 * f + 1, 2 * f)]
         else:
             out.append(torch.stack([p1, p4, p5])[None])
-            nb.append(torch.tensor([-1], dtype=torch.long))
-            count += 1
-    return torch.cat(out, dim=0), torch.cat(nb, dim=0)
+            key.append(torch.tensor([2 * f]))
+    cv, key = torch.cat(out, dim=0), torch.cat(key)
+    order = torch.argsort(key)            # the reference's order: faces in mesh order, t1 before t2
+    cv, key = cv[order], key[order]
+    where = {int(k): i for i, k in enumerate(key.tolist())}
+    nbv = torch.full((len(key),), -1, dtype=torch.long)
+    for a, b in mates:
+        nbv[where[a]] = where[b]
+    return cv, nbv
 
 
-def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
-    """Soft silhouette alpha for the pixel rows ``rows`` (1-D long tensor): (len(rows), S)."""
+def frozen_hit_masks(scene, S, action, el0, az0, radius, blur, K):
+    """Per object, the (S*S, Fc) boolean matrix "clipped face c is one of the kept hits of pixel p" as the fp32 oracle
+    decides it (culls, hit tests, the neighbour rule of cut quadrilaterals, the nearest-K cut).  Where a decision
+    is a tie that only rounding breaks -- a pixel inside one triangle of a cut quadrilateral whose nearest edge is the
+    shared diagonal sees the SAME distance from both triangles -- float64 would decide differently from the fp32
+    reference; the gradient oracle therefore differentiates through the reference's own discrete decisions, which
+    is also what autograd does in pytorch3d."""
+    from . import oracle as O
+    _, _, _, R, T = O.pose_step(np.asarray(action, np.float32), np.float32(el0), np.float32(az0), np.float32(radius))
+    vproj = O.project(scene.verts, R, T)
+    masks = []
+    for i in range(scene.n_obj):
+        v0, v1 = int(scene.obj_vert_start[i]), int(scene.obj_vert_start[i + 1])
+        f0, f1 = int(scene.obj_face_start[i]), int(scene.obj_face_start[i + 1])
+        fv = vproj[v0:v1][scene.faces[f0:f1] - v0]
+        if (fv[:, :, 2] < O.Z_CLIP).any():
+            cv, _, nb, _ = O.clip_faces(fv)
+            fr = O.rasterize_fv(cv, nb, S, blur, K)
+        else:
+            cv = fv
+            fr = O.rasterize_fv(fv, None, S, blur, K)
+        m = np.zeros((S * S, len(cv)), bool)
+        p2f = fr.pix_to_face.reshape(S * S, -1)
+        pix, k = np.nonzero(p2f >= 0)
+        m[pix, p2f[pix, k]] = True
+        masks.append(torch.from_numpy(m))
+    return masks
+
+
+def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True, hit_mask=None):
+    """Soft silhouette alpha for the pixel rows ``rows`` (1-D long tensor): (len(rows), S).  ``hit_mask`` (S*S, Fc):
+    the kept hits are given (``frozen_hit_masks``) instead of being decided here."""
     dtype = vproj.dtype
     fv = vproj[faces]  # (F,3,3)
     nb = None
@@ -167,6 +203,10 @@ def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
     dist = torch.minimum(torch.minimum(_seg(PX, PY, x0, y0, x1, y1), _seg(PX, PY, x0, y0, x2, y2)),
                          _seg(PX, PY, x1, y1, x2, y2))
     hit = in_box & (pz >= 0) & (inside | (dist < blur))
+    if hit_mask is not None:
+        pix = (rows[:, None] * S + torch.arange(S)[None, :]).reshape(-1)
+        hit = hit_mask[pix][:, idx]
+        nb = None
     if nb is not None:
         # clipped_faces_neighbor_idx: of the two triangles of a cut quadrilateral hitting one pixel only the one with
         # the smaller distance is kept (the first on ties), as the face loop of the reference does
@@ -181,7 +221,7 @@ def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
             lose = hit[:, m] & has[None, :] & torch.where(first, d_mate < d_self, d_mate <= d_self)
             hit = hit & ~lose
     nh = hit.sum(dim=1)
-    if int(nh.max()) > K:
+    if hit_mask is None and int(nh.max()) > K:
         # keep the K nearest by (pz, face index): stable sort on pz keeps the lower index first on ties
         key = torch.where(hit, pz.detach(), torch.full_like(pz, float("inf")))
         order = torch.sort(key, dim=1, stable=True).indices
@@ -195,7 +235,7 @@ def soft_alpha_rows(vproj, faces, S, rows, blur, sigma, K, cull=True):
 
 
 def occlusion_loss(verts, faces, obj_face_start, obj_vert_start, S, R, T, s, blur, sigma, K, row_chunk=16,
-                   backward=False):
+                   backward=False, hit_masks=None):
     """loss = sum_px (sum_{i<j} A_i A_j)^2 (``environment.py:373,381``), evaluated in row chunks.  With
     ``backward=True`` every chunk is back-propagated immediately (the graph of one chunk is alive at a
     time) and the float value is returned; otherwise a differentiable tensor is returned."""
@@ -210,7 +250,8 @@ def occlusion_loss(verts, faces, obj_face_start, obj_vert_start, S, R, T, s, blu
         for i in range(n_obj):
             v0, v1 = int(obj_vert_start[i]), int(obj_vert_start[i + 1])
             f0, f1 = int(obj_face_start[i]), int(obj_face_start[i + 1])
-            A.append(soft_alpha_rows(vproj[v0:v1], faces[f0:f1] - v0, S, rows, blur, sigma, K))
+            A.append(soft_alpha_rows(vproj[v0:v1], faces[f0:f1] - v0, S, rows, blur, sigma, K,
+                                     hit_mask=None if hit_masks is None else hit_masks[i]))
         occl = torch.zeros_like(A[0])
         for i in range(n_obj):
             for j in range(i + 1, n_obj):
@@ -228,16 +269,18 @@ def occlusion_loss(verts, faces, obj_face_start, obj_vert_start, S, R, T, s, blu
 
 
 def reward_and_grad(scene, S, action, el0, az0, radius, prev_loss, mass, s, blur, sigma, K=100, step_size=0.05,
-                    dtype=torch.float64):
+                    dtype=torch.float64, freeze_hits=False):
     """d reward / d action for one env by autograd (``environment.py:352-392`` in one differentiable
-    graph).  Returns (reward, loss, grad_action (2,), alphas)."""
+    graph).  Returns (reward, loss, grad_action (2,), alphas).  ``freeze_hits``: take the discrete decisions from the
+    fp32 oracle (needed when faces are cut at z_clip, see ``frozen_hit_masks``)."""
     verts = torch.tensor(scene.verts, dtype=dtype)
     faces = torch.tensor(scene.faces, dtype=torch.long)
     a = torch.tensor(np.asarray(action), dtype=dtype, requires_grad=True)
     el, az, C, R, T = pose_step(a, torch.tensor(float(el0), dtype=dtype), torch.tensor(float(az0), dtype=dtype),
                                 torch.tensor(float(radius), dtype=dtype), step_size)
+    masks = frozen_hit_masks(scene, S, action, el0, az0, radius, blur, K) if freeze_hits else None
     loss_val, alphas = occlusion_loss(verts, faces, scene.obj_face_start, scene.obj_vert_start, S, R, T, s, blur,
-                                      sigma, K, backward=True)
+                                      sigma, K, backward=True, hit_masks=masks)
     # reward = (prev - loss)/mass + const  ->  d reward / d a = -(d loss / d a) / mass
     g = a.grad if a.grad is not None else torch.zeros_like(a)
     reward = (prev_loss - loss_val) / mass

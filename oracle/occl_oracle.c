@@ -77,10 +77,33 @@ void occl_oracle_look_at(const float C[3], float R[9], float T[3]) {
   T[2] = -((z[0] * C[0] + z[1] * C[1]) + z[2] * C[2]);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Switches for the restatement's DISCRETIONARY choices: places where pytorch3d gives no bit-level definition     */
+/* (or where its definition cannot run on both CPU and GPU bit-identically).  The default of every switch is what */
+/* the CUDA kernels implement; tools/pin_with_pytorch3d.py flips them one at a time on a machine that has the real */
+/* library to tell WHICH choice differs from it (DESIGN.md section 3 lists them).                                  */
+/* ------------------------------------------------------------------------------------------ */
+enum {
+  OCCL_OPT_TRIG_FP32 = 0,        /* 0: sin/cos in double, rounded once (default) ; 1: fp32 sinf/cosf like torch.sin on CPU */
+  OCCL_OPT_PROJ_MATRIX = 1,      /* 0: x_ndc = (s x_view) / z_view with ((xR00 + yR10) + zR20) + T0 (default) ;
+                                    1: one composed 4x4 (world->view->ndc) applied to (x, y, z, 1), then / w, as
+                                       Transform3d.compose(...).transform_points does (row-vector bmm, k ascending) */
+  OCCL_OPT_NEIGHBOR_TOPK = 2,    /* 0: a cut quadrilateral's triangles are matched among ALL hits of the pixel (default) ;
+                                    1: only among the current <= K nearest, as pytorch3d's per-pixel queue does */
+  OCCL_OPT_COUNT = 3
+};
+static int g_opt[OCCL_OPT_COUNT] = {0, 0, 0};
+int occl_oracle_set_option(int key, int value) {
+  if (key < 0 || key >= OCCL_OPT_COUNT) return -1;
+  g_opt[key] = value;
+  return 0;
+}
+int occl_oracle_get_option(int key) { return key >= 0 && key < OCCL_OPT_COUNT ? g_opt[key] : -1; }
+
 /* Trigonometry is evaluated in double and rounded once to fp32 so that the CPU restatement and
  * the device path agree bit-for-bit (fp32 sinf/cosf differ between libm and CUDA by ulps). */
-static float sin32(float a) { return (float)sin((double)a); }
-static float cos32(float a) { return (float)cos((double)a); }
+static float sin32(float a) { return g_opt[OCCL_OPT_TRIG_FP32] ? sinf(a) : (float)sin((double)a); }
+static float cos32(float a) { return g_opt[OCCL_OPT_TRIG_FP32] ? cosf(a) : (float)cos((double)a); }
 
 /* environment.py:356-365: normalise action, integrate the angles, step-convention camera centre. */
 void occl_oracle_pose_step(const float action[2], float step_size, float radius, float* el,
@@ -114,6 +137,27 @@ void occl_oracle_pose_lookat(float dist, float elev, float azim, float C[3], flo
  * (environment.py:238): X_view = X_world R + T; ndc.xy = s * view.xy / view.z; ndc.z := view.z. */
 void occl_oracle_project(const float* verts, int V, const float R[9], const float T[3], float s,
                          float* out) {
+  if (g_opt[OCCL_OPT_PROJ_MATRIX]) {
+    /* M = W2V * P (row vectors): W2V = [[R, 0], [T, 1]], P columns x' = s x, y' = s y, w = z; z is read from the
+     * world-to-view transform alone (MeshRasterizer.transform overwrites ndc z with view z). */
+    float M[4][3]; /* columns: x', y', w */
+    for (int r = 0; r < 3; ++r) {
+      M[r][0] = R[r * 3 + 0] * s;
+      M[r][1] = R[r * 3 + 1] * s;
+      M[r][2] = R[r * 3 + 2];
+    }
+    M[3][0] = T[0] * s; M[3][1] = T[1] * s; M[3][2] = T[2];
+    for (int v = 0; v < V; ++v) {
+      const float x = verts[v * 3 + 0], y = verts[v * 3 + 1], z = verts[v * 3 + 2];
+      const float xp = ((x * M[0][0] + y * M[1][0]) + z * M[2][0]) + M[3][0];
+      const float yp = ((x * M[0][1] + y * M[1][1]) + z * M[2][1]) + M[3][1];
+      const float w = ((x * M[0][2] + y * M[1][2]) + z * M[2][2]) + M[3][2];
+      out[v * 3 + 0] = xp / w;
+      out[v * 3 + 1] = yp / w;
+      out[v * 3 + 2] = ((x * R[2] + y * R[5]) + z * R[8]) + T[2];
+    }
+    return;
+  }
   for (int v = 0; v < V; ++v) {
     const float x = verts[v * 3 + 0], y = verts[v * 3 + 1], z = verts[v * 3 + 2];
     float xv = ((x * R[0] + y * R[3]) + z * R[6]) + T[0];
@@ -289,7 +333,7 @@ void occl_oracle_rasterize_fv(const float* face_verts, const int32_t* neighbor, 
     const float yf = pix_to_ndc(S - 1 - yi, S);
     for (int xi = 0; xi < S; ++xi) {
       const float xf = pix_to_ndc(S - 1 - xi, S);
-      size_t n = 0;
+      size_t n = 0, n_all = 0;
       for (int f = 0; f < F; ++f) {
         hit_t h;
         if (!eval_pixel_face(&fc[f], xf, yf, blur_radius, persp, clip_bary, &h)) continue;
@@ -308,8 +352,15 @@ void occl_oracle_rasterize_fv(const float* face_verts, const int32_t* neighbor, 
           q = (hit_t*)realloc(q, sizeof(hit_t) * cap);
         }
         q[n++] = h;
+        ++n_all;
+        if (g_opt[OCCL_OPT_NEIGHBOR_TOPK] && n > (size_t)K) {
+          /* pytorch3d's per-pixel queue: never more than K entries -- the farthest is dropped at once, so a later
+           * neighbour triangle is only matched against what is still among the K nearest */
+          qsort(q, n, sizeof(hit_t), hit_cmp);
+          n = (size_t)K;
+        }
       }
-      if (nhits) nhits[(size_t)yi * S + xi] = (int32_t)n;
+      if (nhits) nhits[(size_t)yi * S + xi] = (int32_t)n_all;
       if (n == 0) continue;
       /* keeping the K smallest tuples == the reference's sort-and-pop_back deque */
       qsort(q, n, sizeof(hit_t), hit_cmp);

@@ -80,6 +80,34 @@ PROJ_SCALE = fov_scale()
 # ------------------------------------------------------------------------------------------------
 # thin wrappers
 # ------------------------------------------------------------------------------------------------
+# Switches for the discretionary choices of the restatement (see occl_oracle.c); defaults = what the kernels implement.
+OPT_TRIG_FP32, OPT_PROJ_MATRIX, OPT_NEIGHBOR_TOPK = 0, 1, 2
+OPTIONS = {"trig_fp32": OPT_TRIG_FP32, "proj_matrix": OPT_PROJ_MATRIX, "neighbor_topk": OPT_NEIGHBOR_TOPK}
+_PY_OPTIONS = {"clip_lerp_ndc": 0, "specular_center_inverse": 0}
+
+
+def set_option(name: str, value: int) -> None:
+    """``trig_fp32``: sin/cos in fp32 libm instead of double-rounded-once; ``proj_matrix``: one composed 4x4 applied to
+    (x, y, z, 1) then / w instead of (s x_view) / z_view; ``neighbor_topk``: cut-quadrilateral triangles matched only
+    among the current <= K nearest hits; ``clip_lerp_ndc``: clip_faces interpolates the cut vertex as
+    p1 + w (p - p1) on (x z, y z) in one fused expression order (a + w*(b - a)) instead of a*(1-w) + b*w;
+    ``specular_center_inverse``: camera centre for the specular term recovered as -T R^-1 (4x4 inverse route of
+    cameras.get_camera_center()) instead of the look-at position C."""
+    if name in OPTIONS:
+        if lib().occl_oracle_set_option(OPTIONS[name], int(value)) != 0:
+            raise ValueError(name)
+    elif name in _PY_OPTIONS:
+        _PY_OPTIONS[name] = int(value)
+    else:
+        raise ValueError(f"unknown oracle option {name!r}")
+
+
+def get_options() -> dict:
+    d = {k: int(lib().occl_oracle_get_option(v)) for k, v in OPTIONS.items()}
+    d.update(_PY_OPTIONS)
+    return d
+
+
 def pose_step(action, el, az, radius, step_size=STEP_SIZE):
     """environment.py:356-368.  Returns (el', az', C(3), R(3,3), T(3)) in fp32."""
     a = np.ascontiguousarray(action, np.float32)
@@ -240,6 +268,12 @@ def clip_faces(face_verts, z_clip=Z_CLIP):
         def cut(p):
             w = np.float32((p1[2] - zc) / (p1[2] - p[2]))
             a1 = np.float32(one - w)
+            if _PY_OPTIONS["clip_lerp_ndc"]:  # a + w (b - a)
+                ax, bx = np.float32(p1[0] * p1[2]), np.float32(p[0] * p[2])
+                ay, by = np.float32(p1[1] * p1[2]), np.float32(p[1] * p[2])
+                x = np.float32(np.float32(ax + np.float32(w * np.float32(bx - ax))) / zc)
+                y = np.float32(np.float32(ay + np.float32(w * np.float32(by - ay))) / zc)
+                return np.array([x, y, zc], np.float32), w
             x = np.float32(np.float32(np.float32(p1[0] * p1[2]) * a1 + np.float32(np.float32(p[0] * p[2]) * w)) / zc)
             y = np.float32(np.float32(np.float32(p1[1] * p1[2]) * a1 + np.float32(np.float32(p[1] * p[2]) * w)) / zc)
             return np.array([x, y, zc], np.float32), w
@@ -329,7 +363,14 @@ def render_scene(verts, faces, obj_face_start, obj_vert_start, S, C, R, T, s=PRO
     objs = np.sum(alphas.astype(np.float32), axis=0)
     objects_sq = np.float32(np.sum(objs.astype(np.float64) ** 2))
     scene = rasterize_clipped(vproj, faces, S, 0.0, 1)           # observation settings :267-273
-    obs = flat_shade(verts, faces, scene, C, light)
+    cam_center = C
+    if _PY_OPTIONS["specular_center_inverse"]:
+        # cameras.get_camera_center(): the world-to-view 4x4 [[R, 0], [T, 1]] inverted in fp32, centre = last row
+        M = np.eye(4, dtype=np.float32)
+        M[:3, :3] = np.asarray(R, np.float32)
+        M[3, :3] = np.asarray(T, np.float32)
+        cam_center = np.linalg.inv(M).astype(np.float32)[3, :3]
+    obs = flat_shade(verts, faces, scene, cam_center, light)
     p2f = scene.pix_to_face[..., 0]
     n_vis = [int(((p2f >= obj_face_start[i]) & (p2f < obj_face_start[i + 1])).sum()) for i in range(n_obj)]
     return RenderOut(obs, alphas, occl, loss, objects_sq, p2f, scene.zbuf[..., 0], scene.bary[..., 0, :],

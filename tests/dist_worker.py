@@ -60,6 +60,29 @@ def main():
                 if not torch.equal(got, want):
                     ok = False
                     print(f"step {t}: gathered {name} is not the rank-ordered full batch", flush=True)
+    # 4. the fused transport: the rasteriser stores the observation rows straight into the learner's HBM (peer memory
+    #    over NVLink), compact 2-plane layout; only reward + done go through NCCL
+    from occlusionenv_b200.config import RasterConfig
+    from occlusionenv_b200.dist import expand_compact_obs
+    mine2 = BatchedOcclusionVecEnv(n_local, data="box", img_size=S, device=dev, auto_reset=False, env_offset=lo,
+                                   cfg=RasterConfig(image_size=S, obs_planes=2))
+    full.engine.reset(radius=4.0, azimuth=az, elevation=el)
+    mine2.engine.reset(radius=4.0, azimuth=az[lo:hi], elevation=el[lo:hi])
+    lg2 = LearnerGather(n_local, (2, S, S), dev, dst=0, transport="p2p")
+    peer_obs = lg2.obs_send_buffer()
+    for t in range(2):
+        a_all = actions[t % 8]
+        f_obs, f_rew, _, _ = full.step(a_all.to(dev))
+        mine2.engine.step(a_all[lo:hi].to(dev), obs=peer_obs)
+        g_obs, g_rew, g_done = lg2.gather(peer_obs, mine2.engine.reward, mine2.engine.done)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            if not (torch.equal(expand_compact_obs(g_obs), f_obs) and torch.equal(g_rew, f_rew)
+                    and torch.equal(g_done, full.engine.done)):
+                ok = False
+                print(f"step {t}: peer-memory delivery differs from the full batch", flush=True)
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

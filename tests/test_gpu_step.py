@@ -440,12 +440,42 @@ def test_configuration_variants_match_oracle(oracle, cuda_lib, variant):
         assert (np.stack(nhits) > K).any()
     if variant.startswith("near_camera_clip"):
         np.testing.assert_allclose(eng.bary[0].cpu().numpy(), scene.bary[..., 0, :], rtol=1e-5, atol=1e-6)
-        # gradients through cut faces are not implemented: the differentiable step flags the frame and the host raises
-        from occlusionenv_b200 import _lib as L
+        # the differentiable step takes cut faces too (test_gradient_through_faces_cut_at_z_clip checks the values)
         eng.step(torch.zeros(1, 2, device="cuda"), with_grad=True)
-        assert int(eng.status[0]) & 1
-        with pytest.raises(L.OcclError):
-            eng.check_status()
+        assert not (int(eng.status[0]) & 1) and (int(eng.status[0]) & 16)
+        eng.check_status()
+        assert torch.isfinite(eng.grad_action).all()
+
+
+def test_gradient_through_faces_cut_at_z_clip(oracle, cuda_lib):
+    """Camera so close that faces straddle z_clip = znear / 2 (clip_faces cases 3 / 4) AND the objects occlude each
+    other: d reward / d action through the cut triangles -- their plane intersections move with x, y and z of the
+    uncut vertices -- against float64 autograd of the clip-aware dense formulation, 1e-3 relative.  The discrete
+    decisions (hit sets, the neighbour rule on the shared diagonal of a cut quadrilateral, nearest K) are the fp32
+    oracle's in both, see oracle/dense_torch.py::frozen_hit_masks."""
+    from oracle import dense_torch as D
+    sc = default_scene("teapot")
+    S = 48
+    cases = [(1.8, 1.5, 0.3, (0.3, -0.4)), (1.8, 1.8, 0.3, (-1.0, 0.2)), (2.2, 1.5, 0.3, (0.5, 0.5)), (2.2, 1.8, 0.0, (0.0, 1.0))]
+    n = len(cases)
+    eng = _engine(sc, n, S)
+    eng.set_pose(torch.tensor([c[0] for c in cases]), torch.tensor([c[1] for c in cases]), torch.tensor([c[2] for c in cases]))
+    eng.full_reward.zero_()
+    eng.object_mass.fill_(1.0)
+    act = np.array([c[3] for c in cases], np.float32)
+    eng.step(torch.tensor(act, device="cuda"), with_grad=True)
+    st = eng.status.cpu().numpy()
+    assert (st & 16).all(), "every case must cut faces"
+    assert not (st & (1 | 4 | 8)).any()
+    eng.check_status()
+    g_gpu = eng.grad_action.cpu().numpy()
+    for e, (r, az, el, a) in enumerate(cases):
+        _, loss, g, _ = D.reward_and_grad(sc, S, np.asarray(a, np.float64), el, az, r, 0.0, 1.0, float(oracle.PROJ_SCALE),
+                                          float(oracle.BLUR_RADIUS), float(oracle.SIGMA), freeze_hits=True)
+        assert loss > 1.0, "the case must show occlusion"
+        np.testing.assert_allclose(float(eng.loss[e]), loss, rtol=2e-5)
+        scale = max(np.abs(g).max(), 1e-6)
+        assert np.abs(g_gpu[e] - g).max() <= 1e-3 * scale, (e, g_gpu[e], g)
 
 
 def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
