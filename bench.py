@@ -549,6 +549,36 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
         ms = h.timed(s, K)
         out["step_only"] = {"value": world * N * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K}
 
+    def features_leg():
+        # row N-1: the policy's frozen encoder runs on the env ranks; 256 floats per env travel instead of the image
+        from occlusionenv_b200.dist import FeatureGather
+        from occlusionenv_b200.features import FrozenEncoder, random_state_dict
+        enc = FrozenEncoder(random_state_dict(8), device=dev, chunk=1024)
+        e = OcclusionEngine(sc, N, RasterConfig(image_size=S), device=dev)
+        e.reset(radius=4.0, azimuth=az, elevation=el)
+        fg = FeatureGather(N, enc.out_features, dev, dst=0)
+        feats = torch.empty(N, enc.out_features, dtype=torch.float32, device=dev)
+
+        def s(i):
+            e.step(actions_dev[i % 8])
+            enc(e.obs, out=feats)
+            fg.gather(feats, e.reward, e.done)
+
+        for i in range(warm):
+            s(i)
+        ms = h.timed(s, K)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(3):
+            enc(e.obs, out=feats)
+        ev1.record()
+        torch.cuda.synchronize()
+        out["features"] = {"value": world * N * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
+                           "encoder_ms_per_step": ev0.elapsed_time(ev1) / 3, "bytes_to_learner_per_step": (world - 1) * N * (enc.out_features * 4 + 5),
+                           "encoder": "FullNetwork(8, dilation=2, separable=True).encoder + global average pool, random weights "
+                                      "(the reference's checkpoint is not in its tree), torch/cuDNN convolutions, "
+                                      f"fp32 storage, allow_tf32={bool(torch.backends.cudnn.allow_tf32)}"}
+
     step_only()
     leg("serial", 4, "nccl", 1)
     leg("double_buffered", 4, "nccl", 2)
@@ -557,6 +587,10 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
             leg(name, planes, "p2p", 1)
         except Exception as ex:  # CUDA IPC unavailable (e.g. a container without peer access): reported, not hidden
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    try:
+        features_leg()
+    except Exception as ex:
+        out["features"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     best = max((v["value"] for k, v in out.items() if isinstance(v, dict) and "value" in v and k != "step_only"), default=None)
     out["value"], out["unit"] = best, UNIT
     return out

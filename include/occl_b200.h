@@ -137,6 +137,16 @@ const char* occl_last_cuda_error(void);
  * SubProcVecEnv.py:219).  Idempotent. */
 int occl_enable_peer_access(int peer_device);
 
+/* Map a block another PROCESS exported with cudaIpcGetMemHandle (64-byte handle) into the address space of the
+ * calling process's CURRENT device, peer access to the exporting GPU included (cudaIpcMemLazyEnablePeerAccess).
+ * The returned pointer may be handed to OcclOutputs.obs of a transition running on this device.  (torch's own
+ * CUDA-IPC rebuild maps the block in the EXPORTING device's context of the importing process: its copies work,
+ * kernels of another device fault on it -- measured.) */
+int occl_ipc_open(const void* handle64, void** ptr_out);
+/* The exporting side: the 64-byte CUDA IPC handle of the cudaMalloc block `ptr` lies in, and ptr's offset in it. */
+int occl_ipc_export(const void* ptr, void* handle64_out, size_t* offset_out);
+int occl_ipc_close(void* ptr);
+
 /* Self-test of the rasteriser's division primitive: counts, over n_samples pseudo-random operand
  * pairs of its guarded domain, the results that are not bit-identical to IEEE `a / b`.
  * mismatches_dev: one device u64 (expected 0). */

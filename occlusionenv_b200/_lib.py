@@ -57,7 +57,7 @@ class OcclOutputs(Structure):
 
 
 # every symbol include/occl_b200.h declares
-EXPORTS = ["occl_abi_version", "occl_last_cuda_error", "occl_enable_peer_access", "occl_selftest_div", "occl_config_resolve", "occl_workspace_bytes",
+EXPORTS = ["occl_abi_version", "occl_last_cuda_error", "occl_enable_peer_access", "occl_ipc_open", "occl_ipc_close", "occl_ipc_export", "occl_selftest_div", "occl_config_resolve", "occl_workspace_bytes",
            "occl_workspace_offsets",
            "occl_pose_step", "occl_pose_lookat", "occl_pose_set", "occl_project", "occl_raster",
            "occl_finalize", "occl_step", "occl_reset", "occl_render"]
@@ -86,6 +86,12 @@ def load():
     lib.occl_last_cuda_error.restype = c_char_p
     lib.occl_enable_peer_access.argtypes = [c_int]
     lib.occl_enable_peer_access.restype = c_int
+    lib.occl_ipc_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
+    lib.occl_ipc_open.restype = c_int
+    lib.occl_ipc_export.argtypes = [c_void_p, ctypes.c_char_p, POINTER(c_size_t)]
+    lib.occl_ipc_export.restype = c_int
+    lib.occl_ipc_close.argtypes = [c_void_p]
+    lib.occl_ipc_close.restype = c_int
     lib.occl_selftest_div.argtypes = [ctypes.c_ulonglong, ctypes.c_ulonglong, c_void_p, c_void_p]
     lib.occl_selftest_div.restype = c_int
     lib.occl_config_resolve.argtypes = [P(OcclConfig), c_int]

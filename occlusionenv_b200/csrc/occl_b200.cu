@@ -22,9 +22,11 @@
 // IEEE fp32 add/mul/div/sqrt and NO fused multiply-add: this translation unit is compiled with
 // -fmad=false (see occlusionenv_b200/build.py).  Nothing here falls back to a CPU path.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "occl_b200.h"
 
@@ -310,6 +312,7 @@ struct RasterParams {
   int tidx_cap;
   const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
   const int* clip_list;       // [1 + chunk] number of envs with faces cut at z_clip, then their (chunk-local) ids
+  const int* env_list;        // [1 + chunk] masked transition: number of flagged envs, then their (chunk-local) ids
   // outputs
   float* obs;
   int obs_planes;  // 4: R, G, B, depth planes (reference layout) ; 2: grey, depth (compact transport layout)
@@ -2256,6 +2259,26 @@ raster_kernel(const RasterParams p) {
   raster_tile<GRAD, TW, TH, DBG, false>(p, env, tile);
 }
 
+// Masked transitions (the auto-reset of finished envs inside a step, SubProcVecEnv.py:211-214): usually no env, or a
+// handful, is flagged.  One CTA per (env, tile) of the whole batch would launch 65 536 CTAs that look at a flag and
+// leave (0.2 ms per config-2 step, measured); instead the flagged envs are listed on the device and a fixed grid of
+// CTAs works through the (listed env, tile) items.
+__global__ void mask_list_kernel(const int m, const uint8_t* __restrict__ mask, int* __restrict__ list) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < m && mask[e]) list[1 + atomicAdd(list, 1)] = e;
+}
+
+template <int TW, int TH, bool DBG>
+__global__ void __launch_bounds__(OCCL_THREADS, OCCL_CTAS_FWD) raster_list_kernel(const RasterParams p) {
+  const int n_tiles = p.tiles_x * p.tiles_y;
+  const int n_items = __ldg(p.env_list) * n_tiles;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int env = __ldg(p.env_list + 1 + it / n_tiles);
+    if (!(*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED)) raster_tile<false, TW, TH, DBG, false>(p, env, it % n_tiles);
+    __syncthreads();
+  }
+}
+
 // Envs with cut faces (camera within z_clip = znear/2 of the geometry), which the setup kernel has listed: a fixed
 // grid of CTAs works through the (listed env, tile) items with the clip-capable instantiation of the tile rasteriser
 // (generic tile shape).  With an empty list -- every BASELINE teapot pose -- the few CTAs leave at once.  (One CTA per
@@ -2371,7 +2394,7 @@ static cudaError_t ensure_dyn_smem(size_t smem) {
 }
 
 struct WsLayout {
-  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, clip_list, total;
+  size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, clip_list, env_list, total;
   int tidx_cap;
   int n_tiles;
   int chunk;  // envs rasterised per launch: the per-face scratch (geo .. tile_cnt) is sized for this many, not for N
@@ -2419,6 +2442,49 @@ extern "C" int occl_selftest_div(unsigned long long n_samples, unsigned long lon
 }
 
 extern "C" int occl_abi_version(void) { return OCCL_ABI_VERSION; }
+
+extern "C" int occl_ipc_export(const void* ptr, void* handle64_out, size_t* offset_out) {
+  if (!ptr || !handle64_out || !offset_out) return OCCL_E_INVALID;
+  // cudaIpcGetMemHandle wants the BASE of the cudaMalloc block the pointer lies in (torch's allocator sub-allocates):
+  // the driver knows it (cuMemGetAddressRange), resolved at run time so that the library loads without a driver
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn fn = nullptr;
+  if (!fn) {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = (range_fn)dlsym(h, "cuMemGetAddressRange_v2");
+    if (!fn) {
+      snprintf(g_last_err, sizeof(g_last_err), "libcuda.so.1 / cuMemGetAddressRange_v2 not available");
+      return OCCL_E_CUDA;
+    }
+  }
+  CK(cudaFree(0), "context");  // make sure the runtime's primary context is current for the driver call
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0) {
+    snprintf(g_last_err, sizeof(g_last_err), "cuMemGetAddressRange failed for %p", ptr);
+    return OCCL_E_CUDA;
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base), "cudaIpcGetMemHandle");
+  memcpy(handle64_out, &h, sizeof(h));
+  *offset_out = (size_t)((unsigned long long)(uintptr_t)ptr - base);
+  return OCCL_OK;
+}
+
+extern "C" int occl_ipc_open(const void* handle64, void** ptr_out) {
+  if (!handle64 || !ptr_out) return OCCL_E_INVALID;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(&h, handle64, sizeof(h));
+  // mapped into the CURRENT device's address space, peer access to the exporting device enabled as needed
+  CK(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  return OCCL_OK;
+}
+
+extern "C" int occl_ipc_close(void* ptr) {
+  CK(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle");
+  return OCCL_OK;
+}
 
 extern "C" int occl_enable_peer_access(int peer_device) {
   int dev = 0;
@@ -2509,6 +2575,7 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->tile_idx = off; off = align_up(off + sizeof(int) * m * L->n_tiles * L->tidx_cap, 256);
   L->tile_cnt = off; off = align_up(off + sizeof(int) * m * L->n_tiles, 256);
   L->clip_list = off; off = align_up(off + sizeof(int) * (m + 1), 256);
+  L->env_list = off; off = align_up(off + sizeof(int) * (m + 1), 256);
   L->set_stride = off - L->geo;
   if (L->sets == 2) off += L->set_stride;
   L->total = off;
@@ -2694,6 +2761,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
       sp.shade = (float2*)(sb + L.shade); sp.tile_idx = p.tile_idx; sp.tile_cnt = bin ? (int*)(sb + L.tile_cnt) : nullptr;
       sp.clip_list = (int*)(sb + L.clip_list); p.clip_list = sp.clip_list;
       CK(cudaMemsetAsync(sp.clip_list, 0, sizeof(int), lane), "memset clip list");
+      p.env_list = (const int*)(sb + L.env_list);
     }
     p.vproj = p0.vproj + e * c.n_verts;
     p.vtan = p0.vtan ? p0.vtan + e * c.n_verts : nullptr;
@@ -2731,7 +2799,23 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     else if (fixed3) OCCL_LAUNCH_RASTER(G, OCCL_TILE3_W, OCCL_TILE3_H, true);                   \
     else OCCL_LAUNCH_RASTER(G, 0, 0, true);                                                     \
   } while (0)
-    if (grad) OCCL_LAUNCH_RASTER_G(true); else OCCL_LAUNCH_RASTER_G(false);
+    if (p.env_mask && !grad) {
+      // masked transition: list the flagged envs, then a fixed grid over (listed env, tile)
+      int* el = (int*)p.env_list;
+      CK(cudaMemsetAsync(el, 0, sizeof(int), lane), "memset env list");
+      mask_list_kernel<<<(m + 255) / 256, 256, 0, lane>>>(m, p.env_mask, el);
+      const unsigned lgrid = (unsigned)(blocks < 4 * 148 ? blocks : 4 * 148);
+#define OCCL_LAUNCH_LIST(W, H, D)                                                              \
+  do {                                                                                         \
+    CK((ensure_dyn_smem<raster_list_kernel<W, H, D>>(smem)), "smem attr");                      \
+    raster_list_kernel<W, H, D><<<lgrid, OCCL_THREADS, smem, lane>>>(p);                        \
+  } while (0)
+      if (fixed && !dbg) OCCL_LAUNCH_LIST(OCCL_TILE_W, OCCL_TILE_H, false);
+      else if (fixed2 && !dbg) OCCL_LAUNCH_LIST(OCCL_TILE2_W, OCCL_TILE2_H, false);
+      else if (fixed3 && !dbg) OCCL_LAUNCH_LIST(OCCL_TILE3_W, OCCL_TILE3_H, false);
+      else OCCL_LAUNCH_LIST(0, 0, true);
+#undef OCCL_LAUNCH_LIST
+    } else if (grad) OCCL_LAUNCH_RASTER_G(true); else OCCL_LAUNCH_RASTER_G(false);
 #undef OCCL_LAUNCH_RASTER_G
 #undef OCCL_LAUNCH_RASTER
     // envs with faces cut at z_clip (status bit set by the setup kernel): one CTA per env, generic tile

@@ -53,21 +53,53 @@ def expand_compact_obs(obs2: torch.Tensor) -> torch.Tensor:
     return obs2[:, (0, 0, 0, 1)]
 
 
+class PeerView:
+    """A (slice of a) float32 tensor that lives in ANOTHER GPU's memory, mapped into this process with CUDA IPC on this
+    rank's own device.  It only carries the address: ``engine.step(..., obs=view)`` lets the rasteriser store its
+    observation rows there (``OcclOutputs.obs``), nothing else in this process reads or writes it."""
+
+    def __init__(self, ptr: int, shape, itemsize: int = 4):
+        self._ptr, self.shape, self._itemsize = int(ptr), tuple(shape), itemsize
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def __getitem__(self, sl: slice) -> "PeerView":
+        lo, hi, step = sl.indices(self.shape[0])
+        assert step == 1
+        row = self._itemsize
+        for d in self.shape[1:]:
+            row *= d
+        return PeerView(self._ptr + lo * row, (hi - lo,) + self.shape[1:], self._itemsize)
+
+
+_IPC_OPENED = {}  # exported block (64-byte handle) -> base address in this process
+
+
 def _share_cuda_tensor(t: Optional[torch.Tensor], src: int):
-    """Map ``t`` (allocated on rank ``src``) into every other rank's address space through CUDA IPC; returns a
-    tensor aliasing the same device memory (peer access over NVLink).  On ``src`` it is ``t`` itself."""
-    from torch.multiprocessing.reductions import reduce_tensor
-    box = [reduce_tensor(t) if dist.get_rank() == src else None]
+    """Map ``t`` (a contiguous float32 tensor allocated on rank ``src``) into every other rank's address space through
+    CUDA IPC, opened on the importing rank's OWN device (peer access over NVLink / NVSwitch).  Returns ``t`` on ``src``
+    and a ``PeerView`` elsewhere."""
+    import ctypes
+
+    from . import _lib as L
+    meta = None
+    if dist.get_rank() == src:
+        assert t.is_contiguous() and t.dtype == torch.float32
+        hbuf, off = ctypes.create_string_buffer(64), ctypes.c_size_t()
+        L.check(L.load().occl_ipc_export(ctypes.c_void_p(t.data_ptr()), hbuf, ctypes.byref(off)), "occl_ipc_export")
+        meta = (hbuf.raw, int(off.value), tuple(t.shape))
+    box = [meta]
     dist.broadcast_object_list(box, src=src)
     if dist.get_rank() == src:
         return t
-    fn, args = box[0]
-    peer = fn(*args)
-    # torch maps the block in the exporting device's context of THIS process; kernels of this rank's own device need
-    # peer access to it (torch only enables that for its own copies)
-    from . import _lib as L
-    L.check(L.load().occl_enable_peer_access(int(peer.device.index)), "occl_enable_peer_access")
-    return peer
+    handle, offset, shape = box[0]
+    base = _IPC_OPENED.get(handle)
+    if base is None:
+        out = ctypes.c_void_p()
+        L.check(L.load().occl_ipc_open(handle, ctypes.byref(out)), "occl_ipc_open")
+        base = _IPC_OPENED[handle] = int(out.value)
+    return PeerView(base + offset, shape)
 
 
 class LearnerGather:
@@ -134,7 +166,9 @@ class LearnerGather:
         g_obs = self._g_obs[self._cur] if (learner or self.transport == "p2p") else None
         move_obs = not (self.transport == "p2p" and in_place)
         if self.transport == "p2p" and not in_place:
-            g_obs[self._slice].copy_(obs)  # peer store of a tensor rendered elsewhere
+            if not learner:
+                raise ValueError("p2p transport: render into obs_send_buffer() (engine.step(..., obs=buffer))")
+            g_obs[self._slice].copy_(obs)
             move_obs = False
         if dist.get_backend() != "nccl":
             return self._gather_collective(obs, reward, done, move_obs)
@@ -189,3 +223,40 @@ class LearnerGather:
         for i, t in enumerate((obs, reward, done.to(torch.uint8))):
             dist.all_gather_into_tensor(self._all[i], t.contiguous())
         return self._all
+
+
+class FeatureGather:
+    """Row N-1: the env ranks run the policy's frozen encoder (occlusionenv_b200/features.py) on
+    the observations they render and the learner receives (N_total, n_features) pooled features + reward + done --
+    1 029 B/env instead of 262 149 B/env at 128^2 -- in one grouped NCCL transfer."""
+
+    def __init__(self, n_local: int, n_features: int, device, dst: int = 0):
+        self.world, self.rank, self.dst, self.n_local = dist.get_world_size(), dist.get_rank(), dst, n_local
+        n = n_local * self.world
+        self._bufs = None
+        if self.rank == dst:
+            self._bufs = (torch.empty(n, n_features, dtype=torch.float32, device=device),
+                          torch.empty(n, dtype=torch.float32, device=device),
+                          torch.empty(n, dtype=torch.uint8, device=device))
+
+    def gather(self, features: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+        done = done if done.dtype == torch.uint8 else done.to(torch.uint8)
+        tensors = (features.contiguous(), reward.contiguous(), done.contiguous())
+        if dist.get_backend() != "nccl":
+            for i, t in enumerate(tensors):
+                dist.gather(t, list(self._bufs[i].chunk(self.world, dim=0)) if self.rank == self.dst else None, dst=self.dst)
+            return self._bufs if self.rank == self.dst else (None, None, None)
+        ops = []
+        if self.rank == self.dst:
+            for r in range(self.world):
+                sl = slice(r * self.n_local, (r + 1) * self.n_local)
+                for i, t in enumerate(tensors):
+                    if r == self.rank:
+                        self._bufs[i][sl].copy_(t)
+                    else:
+                        ops.append(dist.P2POp(dist.irecv, self._bufs[i][sl], r))
+        else:
+            ops = [dist.P2POp(dist.isend, t, self.dst) for t in tensors]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return self._bufs if self.rank == self.dst else (None, None, None)
