@@ -357,9 +357,13 @@ def run_ours(args, rank, world, local_rank):
         for i in range(3):
             e2e_step(i)
         ms_ar = h.timed(e2e_step, K)
+        done_frac = float(eng.done.float().mean().item())
         venv.auto_reset = False
         e2e_extra["auto_reset"] = {"value": N * K / (ms_ar * 1e-3), "unit": UNIT, "ms_per_step": ms_ar / K,
-                                   "note": "as e2e, plus the masked device-side auto-reset of finished envs in every step"}
+                                   "done_fraction_last_step": done_frac,
+                                   "note": "as e2e, plus the masked device-side auto-reset of SimpleVecEnv.step_wait: the envs that "
+                                           "finish are re-rendered at the reset pose (azimuth 0: unoccluded, so they finish again at "
+                                           "once, SURVEY B-9) inside the same call -- extra renders, not idle launches"}
         # (3c) a host-side consumer of the observations (datasetGenerator.py, SimpleVecEnv users on the CPU): the
         # whole (N,4,S,S) observation batch is copied to pinned host memory every step as well
         reset()

@@ -88,6 +88,15 @@
 #define HITBUF_CAP (272 * OCCL_WARPS)  /* 2176 */       // hits (12 B each) of one selection round: aliases the face list + depth queue
 #define WQ_CAP 64             // (slot, face) pairs queued per warp for the dense evaluation of a round
 #define RSLOT_CAP 128         // (pixel, object) slots per selection round (table aliases the big-face records)
+// "Evaluate every hit once" (compile-time tiles of at most REC_MAX_TPX pixels: the dense-mesh and many-object tiles):
+// before the main phase the tile counts, per (pixel, object) slot, the faces whose blur box holds the pixel (an upper
+// bound U of its hits: a 2-D difference image + prefix sums); slots with U > K get a segment of U entries in the CTA's
+// slab of HBM scratch and a flag; the main phase then RECORDS (key, term) of every hit on a flagged slot, and the
+// nearest-K rule only has to select.  Slots that did not get a segment fall back to the re-evaluating rounds.
+#define REC_MAX_TPX 512
+#define REC_SLAB_ENTRIES 65536     // (key u64, term f32) entries per resident CTA: 768 KB
+#define REC_SM_MAX 160             // slabs are indexed by (%smid, resident-CTA slot): B200 has 148 SMs
+#define REC_CTAS_PER_SM 4
 #define REC_WORDS 16
 
 static thread_local char g_last_err[256] = "";
@@ -313,6 +322,10 @@ struct RasterParams {
   const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
   const int* clip_list;       // [1 + chunk] number of envs with faces cut at z_clip, then their (chunk-local) ids
   const int* env_list;        // [1 + chunk] masked transition: number of flagged envs, then their (chunk-local) ids
+  // evaluate-once scratch (nullptr: not available): REC_SM_MAX * REC_CTAS_PER_SM slabs of REC_SLAB_ENTRIES entries
+  unsigned long long* rec_keys;
+  float* rec_terms;
+  unsigned* rec_table;        // [REC_SM_MAX] bitmask of the slab slots in use on each SM (zeroed before the launch)
   // outputs
   float* obs;
   int obs_planes;  // 4: R, G, B, depth planes (reference layout) ; 2: grey, depth (compact transport layout)
@@ -1049,6 +1062,15 @@ __device__ __forceinline__ void soft_accumulate(unsigned long long* slot, float 
   atomicAdd(w + 1, term >= 2.0f ? 1u + SOFT_STRONG_ONE : 1u);
   if (covered) atomicOr(w + 1, SOFT_COVERED);
 }
+// the same, returning the slot's meta word as it was before this hit (its count = the hit's position in the slot's
+// recorded segment, its SOFT_ROUND bit = "this slot records", see REC_*)
+__device__ __forceinline__ unsigned soft_accumulate_ret(unsigned long long* slot, float term, bool covered) {
+  unsigned* w = (unsigned*)slot;
+  atomicAdd(w, __float2uint_rn(term * (float)(1u << SOFT_FRAC)));
+  const unsigned old = atomicAdd(w + 1, term >= 2.0f ? 1u + SOFT_STRONG_ONE : 1u);
+  if (covered) atomicOr(w + 1, SOFT_COVERED);
+  return old;
+}
 // product of the factors of an unresolved slot from its fixed-point log sum
 __device__ __forceinline__ float soft_product(unsigned long long w) {
   const unsigned hi = (unsigned)(w >> 32), lo = (unsigned)(w & 0xffffffffull);
@@ -1103,6 +1125,10 @@ __device__ __forceinline__ TileSmem tile_smem_layout(unsigned char* q, const int
   sm.gacc = (unsigned long long*)q;
   sm.defer_n = nullptr;
   return sm;
+}
+// segment table of the evaluate-once path: behind the accumulators (and the tangent sums of the differentiable kernel)
+__device__ __forceinline__ unsigned* tile_smem_seg(const TileSmem& sm, const int tpx, const int n_obj, const bool grad) {
+  return (unsigned*)(sm.soft + (size_t)tpx * n_obj * (grad ? 2 : 1));
 }
 
 __device__ __forceinline__ void load_geo(const uint32_t* __restrict__ rec, FaceGeo* g) {
@@ -1241,10 +1267,28 @@ __device__ __noinline__ void hard_update_cold(unsigned long long* hard, const Ro
   }
 }
 
+// Evaluate-once recording of a hit on a flagged slot: its sort key (clipped-barycentric depth, face index) and its
+// term -log2(1 - prob) go to the slot's segment of the CTA's scratch slab.  Out of line: the hot loop only tests a bit.
+struct RecCtx {
+  const unsigned* seg;          // [n_slots] first entry of the slot's segment
+  unsigned long long* keys;     // this CTA's slab
+  float* terms;
+};
+__device__ __noinline__ void record_hit(const RoundBuf rb, const int f, const float px, const float py, const float term,
+                                        unsigned long long* kdst, float* tdst) {
+  FaceGeo g;
+  round_geo(rb, f, &g);
+  float b0, b1, b2;
+  bary_persp(g, px, py, &b0, &b1, &b2);
+  *kdst = ((unsigned long long)__float_as_uint(pz_clipped(g, b0, b1, b2)) << 32) |
+          (unsigned long long)(rb.hot[f * 4 + 1].z & REC_FIDX_MASK);
+  *tdst = term;
+}
+
 // One (pixel, face) pair: pixel `i` (row-major) of the tile-clipped blur box of round face `f`.
-template <bool GRAD>
+template <bool GRAD, bool REC>
 __device__ __forceinline__ void raster_pair(const RasterParams& p, const TileSmem& sm, const RoundBuf& rb, const int tile_w,
-                                            const int tpx, const int f, const int i) {
+                                            const int tpx, const int f, const int i, const RecCtx& rc) {
   const uint4 a0 = rb.hot[f * 4 + 0], a1 = rb.hot[f * 4 + 1], a2 = rb.hot[f * 4 + 2], a3 = rb.hot[f * 4 + 3];
   const float x0 = __uint_as_float(a0.x), y0 = __uint_as_float(a0.y), x1 = __uint_as_float(a0.z), y1 = __uint_as_float(a0.w);
   const float x2 = __uint_as_float(a1.x), y2 = __uint_as_float(a1.y);
@@ -1311,7 +1355,17 @@ __device__ __forceinline__ void raster_pair(const RasterParams& p, const TileSme
               ly <= (int)((hb >> 24) & 0xff);
   }
   const int obj = (int)((w10 >> REC_OBJ_SHIFT) & 3u);
-  soft_accumulate(sm.soft + (size_t)obj * tpx + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
+  if (REC) {
+    const int slot = obj * tpx + pix;
+    const float term = soft_term(sd, p.inv_sigma_log2e);
+    const unsigned old = soft_accumulate_ret(sm.soft + slot, term, hard_ok);
+    if (old & SOFT_ROUND) {
+      const unsigned pos = rc.seg[slot] + (old & SOFT_CNT_MASK);
+      record_hit(rb, f, px, py, term, rc.keys + pos, rc.terms + pos);
+    }
+  } else {
+    soft_accumulate(sm.soft + (size_t)obj * tpx + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
+  }
   if (hard_ok) {
     bool queued = false;
     if (!have_bary) {
@@ -1390,8 +1444,9 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xff
 // K-overflow resolution of one tile.  Inlined into the kernel (a non-inlined call measured 5-10 % slower on the
 // main phase: ptxas' register allocation of the barrier-free loop is sensitive to what surrounds it); everything
 // is recomputed here so that nothing extra stays live across the caller's main phase.
-template <bool GRAD, int TW, int TH, bool CLIPF>
-__device__ __forceinline__ void koverflow_resolve(const RasterParams p, const int env, const int tile, const int n_tidx) {
+template <bool GRAD, int TW, int TH, bool CLIPF, bool REC>
+__device__ __forceinline__ void koverflow_resolve(const RasterParams p, const int env, const int tile, const int n_tidx,
+                                                  const RecCtx rc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
   const int tpx = tile_w * tile_h;
@@ -1436,6 +1491,95 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       bool any = false;
       for (int i = tid; i < n_slots; i += OCCL_THREADS) any |= (int)((unsigned)(sm.soft[i] >> 32) & SOFT_CNT_MASK) > p.K;
       if (!__syncthreads_or(any)) return;  // the common tile: no pixel has more than K hits
+    }
+    // ---- recorded slots (evaluate-once): the hits are in the slab, a warp per slot only selects --------------------
+    if (REC && rc.keys != nullptr) {
+      constexpr int LIST_CAP = BIG_CAP * REC_WORDS;
+      int* s_list = (int*)sm.big;
+      __shared__ int s_ln, s_lnext, s_lmore;
+      for (;;) {
+        if (tid == 0) { s_ln = 0; s_lnext = 0; s_lmore = 0; }
+        __syncthreads();
+        for (int i = s_begin; i < s_end; ++i) {
+          const unsigned hi = (unsigned)(sm.soft[i] >> 32);
+          const int cnt = (int)(hi & SOFT_CNT_MASK);
+          if (cnt > p.K && (hi & SOFT_ROUND) && !(hi & SOFT_RESOLVED)) {
+            if (soft_strong_shortcut(hi, p.K)) {
+              sm.soft[i] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32);  // product := +0.0f
+              if (GRAD) sm.gacc[i] = 0ull;
+              atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+            } else {
+              const int pos = atomicAdd(&s_ln, 1);
+              if (pos < LIST_CAP) s_list[pos] = i; else s_lmore = 1;
+            }
+          }
+        }
+        __syncthreads();
+        const int ln = min(s_ln, LIST_CAP);
+        const bool more = s_lmore != 0;
+        if (ln > 0) {
+          if (tid == 0) atomicOr(p.status + env, OCCL_ST_KOVERFLOW);
+          for (;;) {
+            int li = 0;
+            if (lane == 0) li = atomicAdd(&s_lnext, 1);
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if (li >= ln) break;
+            const int slot = s_list[li];
+            const unsigned hi = (unsigned)(sm.soft[slot] >> 32);
+            const int nn = (int)(hi & SOFT_CNT_MASK);
+            const unsigned long long* __restrict__ keys = rc.keys + rc.seg[slot];
+            const float* __restrict__ terms = rc.terms + rc.seg[slot];
+            unsigned long long vand = ~0ull, vor = 0ull;
+            for (int i = lane; i < nn; i += 32) { const unsigned long long kx = keys[i]; vand &= kx; vor |= kx; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+              vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+            }
+            const unsigned long long diff = vand ^ vor;
+            const int want = p.K - 1;           // 0-based rank of the last key kept (nn > K here)
+            unsigned long long bound = ~0ull;   // keys < bound are kept
+            if (diff) {
+              const int top = 63 - __clzll((long long)diff);
+              unsigned long long prefix = top == 63 ? 0ull : (vor & ~((2ull << top) - 1ull));
+              bool found = false;
+              for (int bit = top; bit >= 0; --bit) {
+                const unsigned long long m = 1ull << bit;
+                if (!(diff & m)) { prefix |= vand & m; continue; }
+                const unsigned long long cand = prefix | m;
+                int c = 0;
+                for (int i = lane; i < nn; i += 32) c += keys[i] < cand ? 1 : 0;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c <= want) prefix = cand;
+                else if (c == want + 1) { bound = cand; found = true; break; }
+              }
+              if (!found) bound = prefix + 1ull;
+            }
+            const int obj = slot / tpx, pix = slot - obj * tpx;
+            const int ly = pix / tile_w, lx = pix - ly * tile_w;
+            float lsum = 0.f, g0 = 0.f, g1 = 0.f;
+            for (int i = lane; i < nn; i += 32) {
+              const unsigned long long key = keys[i];
+              if (!(key < bound)) continue;
+              lsum += terms[i];
+              if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              lsum += __shfl_down_sync(0xffffffffu, lsum, o);
+              if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
+            }
+            if (lane == 0) {
+              sm.soft[slot] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32) |
+                              (unsigned long long)__float_as_uint(ex2_approx(-lsum));
+              if (GRAD) sm.gacc[slot] = pack2f(g0, g1);
+            }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        if (!more) break;
+      }
     }
     for (;;) {
       int loc = 0, todo = 0, huge = 0;
@@ -1952,6 +2096,114 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   const int tx1 = tx0 + tile_w - 1, ty1 = ty0 + tile_h - 1;
   int* __restrict__ tidx = p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap;
 
+  // ---- evaluate-once pre-pass: which slots can exceed K hits, and where their hits will be recorded -----------
+  constexpr bool REC = !CLIPF && TW * TH > 0 && TW * TH <= REC_MAX_TPX;
+  __shared__ int s_slab;
+  RecCtx rc;
+  rc.seg = nullptr; rc.keys = nullptr; rc.terms = nullptr;
+  if (REC) {
+    if (tid == 0) s_slab = -1;
+    unsigned* seg = tile_smem_seg(sm, tpx, p.n_obj, GRAD);
+    rc.seg = seg;
+    const int n_slots = tpx * p.n_obj;
+    if (binned && n_bin > p.K && p.rec_keys != nullptr) {  // block-uniform
+      const int DW = tile_w + 1, DH = tile_h + 1, DN = DW * DH;
+      int* D = (int*)sm.list;  // [n_obj][DH][DW] difference image of the blur boxes (the round buffers are idle)
+      // (w + 1)(h + 1) <= w h + w + h + 1 <= 2 REC_MAX_TPX + 2 entries per object: fits the aliased region
+      static_assert((size_t)OCCL_MAX_OBJ * (2 * REC_MAX_TPX + 2) * 4 <= (size_t)4 * OCCL_WARPS * WBUF_RECS * REC_WORDS,
+                    "difference image must fit the round buffers");
+      for (int i = tid; i < p.n_obj * DN; i += OCCL_THREADS) D[i] = 0;
+      __syncthreads();
+      for (int c = tid; c < n_bin; c += OCCL_THREADS) {
+        const uint4 rg = __ldg(rng + __ldg(tidx + c));
+        const int x0 = max((int)(rg.x & 0xffffu), tx0) - tx0, x1 = min((int)(rg.x >> 16), tx1) - tx0;
+        const int y0 = max((int)(rg.y & 0xffffu), ty0) - ty0, y1 = min((int)(rg.y >> 16), ty1) - ty0;
+        if (x0 <= x1 && y0 <= y1) {
+          int* Do = D + (int)(rg.w >> 30) * DN;
+          atomicAdd(Do + y0 * DW + x0, 1);
+          atomicAdd(Do + y0 * DW + x1 + 1, -1);
+          atomicAdd(Do + (y1 + 1) * DW + x0, -1);
+          atomicAdd(Do + (y1 + 1) * DW + x1 + 1, 1);
+        }
+      }
+      __syncthreads();
+      for (int r = warp; r < p.n_obj * DH; r += OCCL_WARPS) {  // prefix sums along x, a warp per (object, row)
+        int* row = D + r * DW;
+        int carry = 0;
+        for (int xb = 0; xb < DW; xb += 32) {
+          int v = xb + lane < DW ? row[xb + lane] : 0;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+          }
+          v += carry;
+          if (xb + lane < DW) row[xb + lane] = v;
+          carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < p.n_obj * DW; c += OCCL_THREADS) {  // ... then along y, a thread per (object, column)
+        const int o = c / DW, x = c - o * DW;
+        int acc = 0;
+        for (int y = 0; y < DH; ++y) {
+          acc += D[o * DN + y * DW + x];
+          D[o * DN + y * DW + x] = acc;
+        }
+      }
+      __syncthreads();
+      // segments: slot order, as long as the slab holds them (block scan over the threads' partial sums)
+      const int per = (n_slots + OCCL_THREADS - 1) / OCCL_THREADS;
+      const int b0 = min(tid * per, n_slots), b1 = min(b0 + per, n_slots);
+      int mine = 0;
+      for (int i = b0; i < b1; ++i) {
+        const int o = i / tpx, pix = i - o * tpx, ly = pix / tile_w, lx = pix - ly * tile_w;
+        const int u = D[o * DN + ly * DW + lx];
+        mine += u > p.K ? u : 0;
+      }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int base = incl - mine;
+      for (int w = 0; w < warp; ++w) base += s_wsum[w];
+      bool any_rec = false;
+      for (int i = b0; i < b1; ++i) {
+        const int o = i / tpx, pix = i - o * tpx, ly = pix / tile_w, lx = pix - ly * tile_w;
+        const int u = D[o * DN + ly * DW + lx];
+        if (u > p.K) {
+          if (base + u <= REC_SLAB_ENTRIES) {
+            seg[i] = (unsigned)base;
+            sm.soft[i] = (unsigned long long)SOFT_ROUND << 32;  // "this slot records"
+            any_rec = true;
+          }
+          base += u;
+        }
+      }
+      if (__syncthreads_or(any_rec)) {
+        if (tid == 0) {  // a slab of scratch: one per resident CTA of this SM
+          unsigned smid;
+          asm("mov.u32 %0, %%smid;" : "=r"(smid));
+          if (smid < REC_SM_MAX)
+            for (int b = 0; b < REC_CTAS_PER_SM; ++b)
+              if (!(atomicOr(p.rec_table + smid, 1u << b) & (1u << b))) { s_slab = (int)smid * REC_CTAS_PER_SM + b; break; }
+        }
+        __syncthreads();
+        if (s_slab < 0)  // none free (cannot happen with <= REC_CTAS_PER_SM resident CTAs): record nothing
+          for (int i = b0; i < b1; ++i) sm.soft[i] = 0ull;
+      }
+    }
+    __syncthreads();
+    if (s_slab >= 0) {
+      rc.keys = p.rec_keys + (size_t)s_slab * REC_SLAB_ENTRIES;
+      rc.terms = p.rec_terms + (size_t)s_slab * REC_SLAB_ENTRIES;
+    }
+  }
+
   // ---- main phase: rounds of up to R faces of the tile ----------------------------------------------------
   // A round (a) loads R face records into shared memory, one per thread, and block-scans their pixel counts
   // (pixels of the tile-clipped blur box), then (b) deals the round's (pixel, face) PAIRS evenly to the warps: warp w
@@ -2066,7 +2318,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       for (int jb = w_begin; jb < w_end; jb += 32, j += 32) {
         if (j < w_end) {
           while (j >= fend) { ++f; fstart = fend; fend = rb.pref[f + 1]; }
-          raster_pair<GRAD>(p, sm, rb, tile_w, tpx, f, j - fstart);
+          raster_pair<GRAD, REC>(p, sm, rb, tile_w, tpx, f, j - fstart, rc);
         }
         __syncwarp();
         // dense exact-depth pass over this warp's queued inside hits, before the queue can overflow
@@ -2104,7 +2356,11 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
-  koverflow_resolve<GRAD, TW, TH, CLIPF>(p, env, tile, s_tidx_n);
+  koverflow_resolve<GRAD, TW, TH, CLIPF, REC>(p, env, tile, s_tidx_n, rc);
+  if (REC) {
+    __syncthreads();
+    if (tid == 0 && s_slab >= 0) atomicAnd(p.rec_table + s_slab / REC_CTAS_PER_SM, ~(1u << (s_slab % REC_CTAS_PER_SM)));
+  }
 
   // ---- epilogue: blend, shade, write, reduce ---------------------------------------------------
   const size_t npix = (size_t)S * S;
@@ -2395,6 +2651,7 @@ static cudaError_t ensure_dyn_smem(size_t smem) {
 
 struct WsLayout {
   size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, clip_list, env_list, total;
+  size_t rec_keys, rec_terms, rec_table;  // evaluate-once scratch (0 size when the tile does not record)
   int tidx_cap;
   int n_tiles;
   int chunk;  // envs rasterised per launch: the per-face scratch (geo .. tile_cnt) is sized for this many, not for N
@@ -2402,11 +2659,19 @@ struct WsLayout {
   size_t set_stride;  // bytes from a set-0 scratch buffer to its set-1 twin
 };
 
+// the compile-time tiles of at most REC_MAX_TPX pixels record their hits (see REC_*)
+static bool rec_capable(const OcclConfig* c) {
+  return (c->tile_w == OCCL_TILE2_W && c->tile_h == OCCL_TILE2_H && OCCL_TILE2_W * OCCL_TILE2_H <= REC_MAX_TPX) ||
+         (c->tile_w == OCCL_TILE3_W && c->tile_h == OCCL_TILE3_H && OCCL_TILE3_W * OCCL_TILE3_H <= REC_MAX_TPX) ||
+         (c->tile_w == OCCL_TILE_W && c->tile_h == OCCL_TILE_H && OCCL_TILE_W * OCCL_TILE_H <= REC_MAX_TPX);
+}
+
 static size_t tile_smem_bytes(const OcclConfig* c, int with_grad) {
   const size_t tpx = (size_t)c->tile_w * c->tile_h;
   size_t b = 4 * OCCL_WARPS * WBUF_RECS * REC_WORDS + 4 * OCCL_WARPS * WDEFER_CAP + 4 * BIG_CAP * REC_WORDS + 8 * tpx +
              4 * (size_t)(((c->tile_w + 1) & ~1) + ((c->tile_h + 1) & ~1)) + 8 * tpx * c->n_obj;
   if (with_grad) b += 4 * 2 * tpx * c->n_obj;
+  if (rec_capable(c)) b += 4 * tpx * c->n_obj;  // segment table of the evaluate-once path
   return b;
 }
 
@@ -2578,6 +2843,13 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->env_list = off; off = align_up(off + sizeof(int) * (m + 1), 256);
   L->set_stride = off - L->geo;
   if (L->sets == 2) off += L->set_stride;
+  L->rec_keys = L->rec_terms = L->rec_table = 0;
+  if (rec_capable(c)) {
+    const size_t slabs = (size_t)REC_SM_MAX * REC_CTAS_PER_SM;
+    L->rec_table = off; off = align_up(off + sizeof(unsigned) * REC_SM_MAX, 256);
+    L->rec_keys = off;  off = align_up(off + sizeof(unsigned long long) * slabs * REC_SLAB_ENTRIES, 256);
+    L->rec_terms = off; off = align_up(off + sizeof(float) * slabs * REC_SLAB_ENTRIES, 256);
+  }
   L->total = off;
   return 0;
 }
@@ -2709,6 +2981,13 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.faces = sc.faces; p.faces_stride = sc.faces_env_stride;
   p.cam = (const float*)(base + L.cam);
   p.partials = (Partial*)(base + L.partials);
+  p.rec_keys = nullptr; p.rec_terms = nullptr; p.rec_table = nullptr;
+  if (L.rec_keys) {
+    p.rec_keys = (unsigned long long*)(base + L.rec_keys);
+    p.rec_terms = (float*)(base + L.rec_terms);
+    p.rec_table = (unsigned*)(base + L.rec_table);
+    CK(cudaMemsetAsync(p.rec_table, 0, sizeof(unsigned) * REC_SM_MAX, (cudaStream_t)stream), "memset rec table");
+  }
   p.obs = out.obs; p.obs_planes = c.obs_planes == 2 ? 2 : 4; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
   p.nhits = out.nhits; p.status = out.status; p.env_mask = mask;
   const size_t smem = tile_smem_bytes(&c, grad);

@@ -98,6 +98,9 @@ class OcclusionEnv:
         self.observation_space = Box(0, 1, shape=(4, img_size, img_size))
         self.action_space = Box(low=-0.1, high=0.1, shape=(2,))
         self.renderMode = ""  # 'human'
+        # status flags (selection buffers exceeded, ...) are ORed on the device; reading them costs one 4-byte
+        # device->host copy per call.  Set to False in a tight loop and call ``check_status()`` when convenient.
+        self.check_status_every_step = True
         self.image = None
         self.meshes = None
         self._engine: Optional[OcclusionEngine] = None
@@ -198,7 +201,8 @@ class OcclusionEnv:
         else:
             eng.step(action.detach().to(device=self.device, dtype=torch.float32).reshape(1, 2).contiguous())
             reward = eng.reward.clone()[0]
-        eng.check_status()
+        if self.check_status_every_step:
+            eng.check_status()
         observation = eng.obs.clone()
         self.camera_position = eng.position[0].clone()
         self.image = self._full_state()
@@ -226,6 +230,10 @@ class OcclusionEnv:
             cv2.waitKey(25)
             return None
         return rgba, depth
+
+    def check_status(self) -> int:
+        """Flags raised since the last check (one device word); raises ``OcclError`` on the ones that mean a wrong result."""
+        return self._engine.check_status()
 
     def close(self):
         pass
