@@ -94,7 +94,9 @@
 // slab of HBM scratch and a flag; the main phase then RECORDS (key, term) of every hit on a flagged slot, and the
 // nearest-K rule only has to select.  Slots that did not get a segment fall back to the re-evaluating rounds.
 #define REC_MAX_TPX 512
-#define REC_SLAB_ENTRIES 65536     // (key u64, term f32) entries per resident CTA: 768 KB
+#define REC_SLAB_DENSE 262144      // (key u64, term f32) entries per resident CTA, dense meshes: 3 MB (a 128x4 tile fully
+                                   // covered by two overlapping dense objects needs ~270 k: every slot then records)
+#define REC_SLAB_SPARSE 32768      // ... other scenes: 384 KB
 #define REC_SM_MAX 160             // slabs are indexed by (%smid, resident-CTA slot): B200 has 148 SMs
 #define REC_CTAS_PER_SM 4
 #define REC_WORDS 16
@@ -322,10 +324,11 @@ struct RasterParams {
   const int* tile_cnt;        // [N][n_tiles] faces binned to the tile by the setup kernel (nullptr: more than 256 tiles, no binning)
   const int* clip_list;       // [1 + chunk] number of envs with faces cut at z_clip, then their (chunk-local) ids
   const int* env_list;        // [1 + chunk] masked transition: number of flagged envs, then their (chunk-local) ids
-  // evaluate-once scratch (nullptr: not available): REC_SM_MAX * REC_CTAS_PER_SM slabs of REC_SLAB_ENTRIES entries
+  // evaluate-once scratch (nullptr: not available): REC_SM_MAX * REC_CTAS_PER_SM slabs of rec_cap entries
   unsigned long long* rec_keys;
   float* rec_terms;
   unsigned* rec_table;        // [REC_SM_MAX] bitmask of the slab slots in use on each SM (zeroed before the launch)
+  int rec_cap;                // entries per slab
   // outputs
   float* obs;
   int obs_planes;  // 4: R, G, B, depth planes (reference layout) ; 2: grey, depth (compact transport layout)
@@ -1274,21 +1277,23 @@ struct RecCtx {
   unsigned long long* keys;     // this CTA's slab
   float* terms;
 };
-__device__ __noinline__ void record_hit(const RoundBuf rb, const int f, const float px, const float py, const float term,
-                                        unsigned long long* kdst, float* tdst) {
+__device__ __noinline__ void record_hit(const RoundBuf rb, const int f, const float px, const float py,
+                                        unsigned long long* kdst) {
   FaceGeo g;
   round_geo(rb, f, &g);
   float b0, b1, b2;
   bary_persp(g, px, py, &b0, &b1, &b2);
   *kdst = ((unsigned long long)__float_as_uint(pz_clipped(g, b0, b1, b2)) << 32) |
           (unsigned long long)(rb.hot[f * 4 + 1].z & REC_FIDX_MASK);
-  *tdst = term;
 }
 
 // One (pixel, face) pair: pixel `i` (row-major) of the tile-clipped blur box of round face `f`.
+// REC: a hit on a recording slot stores its term at once and returns (pixel | face << 16, entry) in *rq_word / *rq_pos:
+// the caller queues these per warp and computes the sort keys (nine divisions each) 32 at a time, every lane busy.
 template <bool GRAD, bool REC>
 __device__ __forceinline__ void raster_pair(const RasterParams& p, const TileSmem& sm, const RoundBuf& rb, const int tile_w,
-                                            const int tpx, const int f, const int i, const RecCtx& rc) {
+                                            const int tpx, const int f, const int i, const RecCtx& rc, unsigned* rq_word,
+                                            int* rq_pos) {
   const uint4 a0 = rb.hot[f * 4 + 0], a1 = rb.hot[f * 4 + 1], a2 = rb.hot[f * 4 + 2], a3 = rb.hot[f * 4 + 3];
   const float x0 = __uint_as_float(a0.x), y0 = __uint_as_float(a0.y), x1 = __uint_as_float(a0.z), y1 = __uint_as_float(a0.w);
   const float x2 = __uint_as_float(a1.x), y2 = __uint_as_float(a1.y);
@@ -1361,7 +1366,9 @@ __device__ __forceinline__ void raster_pair(const RasterParams& p, const TileSme
     const unsigned old = soft_accumulate_ret(sm.soft + slot, term, hard_ok);
     if (old & SOFT_ROUND) {
       const unsigned pos = rc.seg[slot] + (old & SOFT_CNT_MASK);
-      record_hit(rb, f, px, py, term, rc.keys + pos, rc.terms + pos);
+      rc.terms[pos] = term;
+      *rq_word = (unsigned)pix | ((unsigned)f << 16);
+      *rq_pos = (int)pos;
     }
   } else {
     soft_accumulate(sm.soft + (size_t)obj * tpx + pix, soft_term(sd, p.inv_sigma_log2e), hard_ok);
@@ -1529,40 +1536,85 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             const int nn = (int)(hi & SOFT_CNT_MASK);
             const unsigned long long* __restrict__ keys = rc.keys + rc.seg[slot];
             const float* __restrict__ terms = rc.terms + rc.seg[slot];
-            unsigned long long vand = ~0ull, vor = 0ull;
-            for (int i = lane; i < nn; i += 32) { const unsigned long long kx = keys[i]; vand &= kx; vor |= kx; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              vand &= __shfl_xor_sync(0xffffffffu, vand, o);
-              vor |= __shfl_xor_sync(0xffffffffu, vor, o);
-            }
-            const unsigned long long diff = vand ^ vor;
-            const int want = p.K - 1;           // 0-based rank of the last key kept (nn > K here)
-            unsigned long long bound = ~0ull;   // keys < bound are kept
-            if (diff) {
-              const int top = 63 - __clzll((long long)diff);
-              unsigned long long prefix = top == 63 ? 0ull : (vor & ~((2ull << top) - 1ull));
-              bool found = false;
-              for (int bit = top; bit >= 0; --bit) {
-                const unsigned long long m = 1ull << bit;
-                if (!(diff & m)) { prefix |= vand & m; continue; }
-                const unsigned long long cand = prefix | m;
-                int c = 0;
-                for (int i = lane; i < nn; i += 32) c += keys[i] < cand ? 1 : 0;
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (c <= want) prefix = cand;
-                else if (c == want + 1) { bound = cand; found = true; break; }
-              }
-              if (!found) bound = prefix + 1ull;
-            }
             const int obj = slot / tpx, pix = slot - obj * tpx;
             const int ly = pix / tile_w, lx = pix - ly * tile_w;
+            const int want = p.K - 1;           // 0-based rank of the last key kept (nn > K here)
             float lsum = 0.f, g0 = 0.f, g1 = 0.f;
-            for (int i = lane; i < nn; i += 32) {
-              const unsigned long long key = keys[i];
-              if (!(key < bound)) continue;
-              lsum += terms[i];
-              if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
+            constexpr int KR = 8;               // keys per lane held in registers: slots of up to 256 hits
+            if (nn <= 32 * KR) {
+              // the slot's keys are read ONCE; the ~12 counting passes of the bisection run on registers
+              unsigned long long kr[KR];
+              unsigned long long vand = ~0ull, vor = 0ull;
+#pragma unroll
+              for (int t = 0; t < KR; ++t) {
+                const int i = lane + 32 * t;
+                kr[t] = i < nn ? keys[i] : ~0ull;   // the padding is larger than every candidate bound
+                if (i < nn) { vand &= kr[t]; vor |= kr[t]; }
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+                vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+              }
+              const unsigned long long diff = vand ^ vor;
+              unsigned long long bound = ~0ull;   // keys < bound are kept
+              if (diff) {
+                const int top = 63 - __clzll((long long)diff);
+                unsigned long long prefix = top == 63 ? 0ull : (vor & ~((2ull << top) - 1ull));
+                bool found = false;
+                for (int bit = top; bit >= 0; --bit) {
+                  const unsigned long long m = 1ull << bit;
+                  if (!(diff & m)) { prefix |= vand & m; continue; }
+                  const unsigned long long cand = prefix | m;
+                  int c = 0;
+#pragma unroll
+                  for (int t = 0; t < KR; ++t) c += kr[t] < cand ? 1 : 0;
+                  c = __reduce_add_sync(0xffffffffu, c);
+                  if (c <= want) prefix = cand;
+                  else if (c == want + 1) { bound = cand; found = true; break; }
+                }
+                if (!found) bound = prefix + 1ull;
+              }
+#pragma unroll
+              for (int t = 0; t < KR; ++t) {
+                const int i = lane + 32 * t;
+                if (i < nn && kr[t] < bound) {
+                  lsum += terms[i];
+                  if (GRAD) hit_tangent(p, env, (int)(kr[t] & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
+                }
+              }
+            } else {
+              unsigned long long vand = ~0ull, vor = 0ull;
+              for (int i = lane; i < nn; i += 32) { const unsigned long long kx = keys[i]; vand &= kx; vor |= kx; }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+                vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+              }
+              const unsigned long long diff = vand ^ vor;
+              unsigned long long bound = ~0ull;
+              if (diff) {
+                const int top = 63 - __clzll((long long)diff);
+                unsigned long long prefix = top == 63 ? 0ull : (vor & ~((2ull << top) - 1ull));
+                bool found = false;
+                for (int bit = top; bit >= 0; --bit) {
+                  const unsigned long long m = 1ull << bit;
+                  if (!(diff & m)) { prefix |= vand & m; continue; }
+                  const unsigned long long cand = prefix | m;
+                  int c = 0;
+                  for (int i = lane; i < nn; i += 32) c += keys[i] < cand ? 1 : 0;
+                  c = __reduce_add_sync(0xffffffffu, c);
+                  if (c <= want) prefix = cand;
+                  else if (c == want + 1) { bound = cand; found = true; break; }
+                }
+                if (!found) bound = prefix + 1ull;
+              }
+              for (int i = lane; i < nn; i += 32) {
+                const unsigned long long key = keys[i];
+                if (!(key < bound)) continue;
+                lsum += terms[i];
+                if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
+              }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -2176,7 +2228,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         const int o = i / tpx, pix = i - o * tpx, ly = pix / tile_w, lx = pix - ly * tile_w;
         const int u = D[o * DN + ly * DW + lx];
         if (u > p.K) {
-          if (base + u <= REC_SLAB_ENTRIES) {
+          if (base + u <= p.rec_cap) {
             seg[i] = (unsigned)base;
             sm.soft[i] = (unsigned long long)SOFT_ROUND << 32;  // "this slot records"
             any_rec = true;
@@ -2199,8 +2251,8 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     }
     __syncthreads();
     if (s_slab >= 0) {
-      rc.keys = p.rec_keys + (size_t)s_slab * REC_SLAB_ENTRIES;
-      rc.terms = p.rec_terms + (size_t)s_slab * REC_SLAB_ENTRIES;
+      rc.keys = p.rec_keys + (size_t)s_slab * p.rec_cap;
+      rc.terms = p.rec_terms + (size_t)s_slab * p.rec_cap;
     }
   }
 
@@ -2222,6 +2274,11 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     rb.cold = (float4*)(rb.hot + R * 4);
     rb.tan = (float4*)(rb.cold + R);
     rb.pref = (int*)(rb.tan + (GRAD ? R * 3 : 0));
+    // recording queues (REC): 47 two-word entries per warp in the spare end of the aliased region
+    constexpr int RQ_CAP = 47;
+    static_assert(!REC || (size_t)R * (64 + 16 + (GRAD ? 48 : 0)) + 4 * (R + 1) + 8 * RQ_CAP * OCCL_WARPS <= (size_t)4 * OCCL_WARPS * WBUF_RECS * REC_WORDS,
+                  "recording queues must fit behind the round buffers");
+    unsigned* rq = (unsigned*)(rb.pref + R + 1) + warp * (2 * RQ_CAP);
     sm.defer = sm.defer + warp * WDEFER_CAP;
     sm.defer_n = &s_wdef_n[warp];
     const int n_src = binned ? n_bin : n_live;
@@ -2314,11 +2371,40 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         f = lo;
       }
       int fstart = rb.pref[f], fend = rb.pref[f + 1];
+      int nrq = 0;  // entries in this warp's recording queue (warp-uniform)
 #pragma unroll 1
       for (int jb = w_begin; jb < w_end; jb += 32, j += 32) {
+        unsigned rq_word = 0u;
+        int rq_pos = -1;
         if (j < w_end) {
           while (j >= fend) { ++f; fstart = fend; fend = rb.pref[f + 1]; }
-          raster_pair<GRAD, REC>(p, sm, rb, tile_w, tpx, f, j - fstart, rc);
+          raster_pair<GRAD, REC>(p, sm, rb, tile_w, tpx, f, j - fstart, rc, &rq_word, &rq_pos);
+        }
+        if (REC) {
+          // recording queue of this warp (positions from a ballot); 32 keys at a time are computed densely
+          const unsigned rqb = __ballot_sync(0xffffffffu, rq_pos >= 0);
+          const bool last_trip = jb + 32 >= w_end;
+          if (rqb || (last_trip && nrq > 0)) {
+            auto drain = [&]() {
+              const int take = min(nrq, 32);
+              nrq -= take;
+              if (lane < take) {
+                const unsigned wd = rq[2 * (nrq + lane)], ps = rq[2 * (nrq + lane) + 1];
+                const int rpix = (int)(wd & 0xffffu), rly = rpix / tile_w, rlx = rpix - rly * tile_w;
+                record_hit(rb, (int)(wd >> 16), sm.ndc_x[rlx], sm.ndc_y[rly], rc.keys + ps);
+              }
+              __syncwarp();
+            };
+            if (nrq + __popc(rqb) > RQ_CAP) drain();  // (at most 31 are waiting: this empties the queue)
+            if (rq_pos >= 0) {
+              const int q = nrq + __popc(rqb & ((1u << lane) - 1u));
+              rq[2 * q] = rq_word;
+              rq[2 * q + 1] = (unsigned)rq_pos;
+            }
+            nrq += __popc(rqb);
+            __syncwarp();
+            while (nrq >= 32 || (last_trip && nrq > 0)) drain();
+          }
         }
         __syncwarp();
         // dense exact-depth pass over this warp's queued inside hits, before the queue can overflow
@@ -2652,6 +2738,7 @@ static cudaError_t ensure_dyn_smem(size_t smem) {
 struct WsLayout {
   size_t cam, vproj, vtan, partials, geo, rng, n_live, tile_mask, shade, tile_idx, tile_cnt, clip_list, env_list, total;
   size_t rec_keys, rec_terms, rec_table;  // evaluate-once scratch (0 size when the tile does not record)
+  int rec_cap;
   int tidx_cap;
   int n_tiles;
   int chunk;  // envs rasterised per launch: the per-face scratch (geo .. tile_cnt) is sized for this many, not for N
@@ -2844,11 +2931,13 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->set_stride = off - L->geo;
   if (L->sets == 2) off += L->set_stride;
   L->rec_keys = L->rec_terms = L->rec_table = 0;
+  L->rec_cap = 0;
   if (rec_capable(c)) {
     const size_t slabs = (size_t)REC_SM_MAX * REC_CTAS_PER_SM;
     L->rec_table = off; off = align_up(off + sizeof(unsigned) * REC_SM_MAX, 256);
-    L->rec_keys = off;  off = align_up(off + sizeof(unsigned long long) * slabs * REC_SLAB_ENTRIES, 256);
-    L->rec_terms = off; off = align_up(off + sizeof(float) * slabs * REC_SLAB_ENTRIES, 256);
+    L->rec_cap = c->n_faces >= OCCL_DENSE_FACES ? REC_SLAB_DENSE : REC_SLAB_SPARSE;
+    L->rec_keys = off;  off = align_up(off + sizeof(unsigned long long) * slabs * L->rec_cap, 256);
+    L->rec_terms = off; off = align_up(off + sizeof(float) * slabs * L->rec_cap, 256);
   }
   L->total = off;
   return 0;
@@ -2981,7 +3070,7 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   p.faces = sc.faces; p.faces_stride = sc.faces_env_stride;
   p.cam = (const float*)(base + L.cam);
   p.partials = (Partial*)(base + L.partials);
-  p.rec_keys = nullptr; p.rec_terms = nullptr; p.rec_table = nullptr;
+  p.rec_keys = nullptr; p.rec_terms = nullptr; p.rec_table = nullptr; p.rec_cap = L.rec_cap;
   if (L.rec_keys) {
     p.rec_keys = (unsigned long long*)(base + L.rec_keys);
     p.rec_terms = (float*)(base + L.rec_terms);
