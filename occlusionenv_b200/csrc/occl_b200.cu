@@ -455,9 +455,11 @@ __device__ __forceinline__ float div_rn_hoisted(float a, float b, float y) {
 __device__ __forceinline__ float pz_clipped(const FaceGeo& g, float b0, float b1, float b2) {
   float c0 = b0 > 0.f ? b0 : 0.f, c1 = b1 > 0.f ? b1 : 0.f, c2 = b2 > 0.f ? b2 : 0.f;
   const float s = fmaxf(c0 + c1 + c2, 1e-5f);
-  c0 = c0 / s;
-  c1 = c1 / s;
-  c2 = c2 / s;
+  // 0 / s is +0 whatever s > 0 is: a clipped (zero) barycentric skips the quotient -- outside hits always have one or two,
+  // and a zero numerator sends the IEEE division down its slow-path subroutine (10 % of the config-3 instructions, measured)
+  c0 = c0 > 0.f ? c0 / s : 0.f;
+  c1 = c1 > 0.f ? c1 / s : 0.f;
+  c2 = c2 > 0.f ? c2 / s : 0.f;
   return c0 * g.z0 + c1 * g.z1 + c2 * g.z2;
 }
 
