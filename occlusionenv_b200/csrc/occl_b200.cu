@@ -1536,7 +1536,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             const int slot = s_list[li];
             const unsigned hi = (unsigned)(sm.soft[slot] >> 32);
             const int nn = (int)(hi & SOFT_CNT_MASK);
-            const unsigned long long* __restrict__ keys = rc.keys + rc.seg[slot];
+            const unsigned long long* keys = rc.keys + rc.seg[slot];
             const float* __restrict__ terms = rc.terms + rc.seg[slot];
             const int obj = slot / tpx, pix = slot - obj * tpx;
             const int ly = pix / tile_w, lx = pix - ly * tile_w;
@@ -1586,6 +1586,15 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
                 }
               }
             } else {
+              // more keys than the registers hold: up to 384 are staged in this warp's share of the (idle) round buffers,
+              // beyond that the counting passes read the slab through L1
+              constexpr int WK = (4 * WBUF_RECS * REC_WORDS) / 8;  // u64 entries per warp
+              if (nn <= WK) {
+                unsigned long long* wk = (unsigned long long*)sm.list + warp * WK;
+                for (int i = lane; i < nn; i += 32) wk[i] = keys[i];
+                __syncwarp();
+                keys = wk;
+              }
               unsigned long long vand = ~0ull, vor = 0ull;
               for (int i = lane; i < nn; i += 32) { const unsigned long long kx = keys[i]; vand &= kx; vor |= kx; }
 #pragma unroll
