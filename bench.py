@@ -477,7 +477,9 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
       double_buffered  two half batches per rank; the transfer of one half (side stream) overlaps the render of the other
       p2p_fused        the rasteriser's epilogue stores the observation rows straight into the learner's HBM over NVLink
                        (peer-mapped gather buffer); only reward + done (5 B/env) go through NCCL
-      p2p_fused_gray   the same with the compact 2-plane observation (grey + depth: the reference's R = G = B)"""
+      p2p_fused_gray   the same with the compact 2-plane observation (grey + depth: the reference's R = G = B)
+      double_buffered_gray  the double-buffered NCCL transfer with the compact observation
+      features         row N-1: the frozen encoder on the env ranks, 256 floats per env to the learner"""
     import torch
     from occlusionenv_b200.config import RasterConfig
     from occlusionenv_b200.dist import LearnerGather
@@ -586,6 +588,7 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
     step_only()
     leg("serial", 4, "nccl", 1)
     leg("double_buffered", 4, "nccl", 2)
+    leg("double_buffered_gray", 2, "nccl", 2)
     for name, planes in (("p2p_fused", 4), ("p2p_fused_gray", 2)):
         try:
             leg(name, planes, "p2p", 1)

@@ -2348,6 +2348,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
           npx = w * (cy1 - cy0 + 1);
           if (CLIPF && (rg.z & RNG_CLIP)) npx = 0;  // cut face (z-clip): rasterised by the clip phase
         }
+
       }
       // exclusive block scan of the pixel counts
       int incl = npx;

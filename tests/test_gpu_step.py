@@ -478,6 +478,35 @@ def test_gradient_through_faces_cut_at_z_clip(oracle, cuda_lib):
         assert np.abs(g_gpu[e] - g).max() <= 1e-3 * scale, (e, g_gpu[e], g)
 
 
+def test_gradient_with_recorded_overflow_slots(oracle, cuda_lib):
+    """Differentiable step on the 32x16 compile-time tile (three objects) with K = 10, so that most covered slots exceed
+    K: the evaluate-once path (hits recorded in the main phase, selection from the slab, tangents of the kept hits
+    re-evaluated by face index) against float64 autograd through the fp32 oracle's nearest-K sets."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    from oracle import dense_torch as D
+    S, K = 64, 10
+    scenes = [procedural_scene(s, n_obj=3, subdiv=3) for s in (2, 3)]
+    n = len(scenes)
+    eng = OcclusionEngine(None, n, RasterConfig(image_size=S, faces_per_pixel=K), per_env_scenes=scenes)
+    assert (int(eng.c.tile_w), int(eng.c.tile_h)) == (32, 16)
+    az0, el0 = np.array([-0.35, 0.3], np.float32), np.array([0.1, 0.1], np.float32)
+    eng.set_pose(4.0, torch.tensor(az0), torch.tensor(el0))
+    eng.full_reward.zero_()
+    eng.object_mass.fill_(1.0)
+    act = np.array([[1.0, 0.5], [-0.3, 0.9]], np.float32)
+    eng.step(torch.tensor(act, device="cuda"), with_grad=True)
+    assert eng.check_status() & 2, "K must be live"
+    g_gpu = eng.grad_action.cpu().numpy()
+    for e, sc in enumerate(scenes):
+        _, loss, g, _ = D.reward_and_grad(sc, S, act[e].astype(np.float64), float(el0[e]), float(az0[e]), 4.0, 0.0, 1.0,
+                                          float(oracle.PROJ_SCALE), float(oracle.BLUR_RADIUS), float(oracle.SIGMA), K=K,
+                                          freeze_hits=True)
+        assert loss > 1.0
+        np.testing.assert_allclose(float(eng.loss[e]), loss, rtol=2e-5)
+        scale = max(np.abs(g).max(), 1e-6)
+        assert np.abs(g_gpu[e] - g).max() <= 1e-3 * scale, (e, g_gpu[e], g)
+
+
 def test_adversarial_triangles_match_oracle(oracle, cuda_lib):
     """Hand-made nasty geometry through occl_render with an identity camera: slivers with one edge shorter
     than 1e-4 (degenerate-edge branch of the point-segment distance), needle triangles, exact duplicates
