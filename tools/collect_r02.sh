@@ -12,6 +12,4 @@ $B > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-c
 B2="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-configs"
 ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 6 -c 1 -f -o gpurun_out/raster_r02 $B2 > gpurun_out/ncu_f.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:face_setup -s 6 -c 1 -f -o gpurun_out/setup_r02 $B2 > gpurun_out/ncu_s.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --grad > gpurun_out/plain_g.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 6 -c 1 -f -o gpurun_out/raster_grad_r02 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --grad > gpurun_out/ncu_g.log 2>&1
-python tools/c3_probe.py 64 256 > gpurun_out/plain_c3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:raster_kernel -s 3 -c 1 -f -o gpurun_out/raster_c3_r02 python tools/c3_probe.py 64 256 > gpurun_out/ncu_c3.log 2>&1
 ls -la gpurun_out/*_r02*.ncu-rep
