@@ -103,6 +103,14 @@
 #define REC_SM_MAX 160             // slabs are indexed by (%smid, resident-CTA slot): B200 has 148 SMs
 #define REC_CTAS_PER_SM 4
 #define REC_WORDS 16
+// observation / occlusion-map stores: written once, read by another kernel (or another GPU) much later
+#ifdef OCCL_STREAMING_STORES
+#define OCCL_STORE(ptr, v) __stcs((ptr), (v))
+#define OCCL_STORE4(ptr, v) __stcs((float4*)(ptr), (v))
+#else
+#define OCCL_STORE(ptr, v) (*(ptr) = (v))
+#define OCCL_STORE4(ptr, v) (*(float4*)(ptr) = (v))
+#endif
 
 static thread_local char g_last_err[256] = "";
 
@@ -2105,15 +2113,15 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         const int xi = tx0 + lx, yi = ty0 + ly;
         if (xi >= S || yi >= S) continue;
         const size_t pix = (size_t)yi * S + xi;
-        *(float4*)(p.occl + (size_t)env * npix + pix) = zero4;
+        OCCL_STORE4(p.occl + (size_t)env * npix + pix, zero4);
         float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
-        *(float4*)(o) = one4;
+        OCCL_STORE4(o, one4);
         if (p.obs_planes == 4) {
-          *(float4*)(o + npix) = one4;
-          *(float4*)(o + 2 * npix) = one4;
-          *(float4*)(o + 3 * npix) = neg4;
+          OCCL_STORE4(o + npix, one4);
+          OCCL_STORE4(o + 2 * npix, one4);
+          OCCL_STORE4(o + 3 * npix, neg4);
         } else {
-          *(float4*)(o + npix) = neg4;
+          OCCL_STORE4(o + npix, neg4);
         }
       }
     } else
@@ -2123,10 +2131,10 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       const int xi = tx0 + lx, yi = ty0 + ly;
       if (xi >= S || yi >= S) continue;
       const size_t pix = (size_t)yi * S + xi;
-      p.occl[(size_t)env * npix + pix] = 0.f;
+      OCCL_STORE(p.occl + (size_t)env * npix + pix, 0.f);
       float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
-      o[0] = 1.0f;
-      if (p.obs_planes == 4) { o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f; } else { o[npix] = -1.0f; }
+      OCCL_STORE(o, 1.0f);
+      if (p.obs_planes == 4) { OCCL_STORE(o + npix, 1.0f); OCCL_STORE(o + 2 * npix, 1.0f); OCCL_STORE(o + 3 * npix, -1.0f); } else { OCCL_STORE(o + npix, -1.0f); }
       for (int ob = 0; ob < p.n_obj; ++ob) {
         if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
         if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
@@ -2489,10 +2497,10 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       for (int o = 0; o < OCCL_MAX_OBJ; ++o)
         if (o < p.n_obj) touched |= (unsigned)(sm.soft[(size_t)o * tpx + i] >> 32);
       if (touched == 0u && key == ~0ull) {
-        p.occl[(size_t)env * npix + pix] = 0.f;
+        OCCL_STORE(p.occl + (size_t)env * npix + pix, 0.f);
         float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
-        o[0] = 1.0f;
-        if (p.obs_planes == 4) { o[npix] = 1.0f; o[2 * npix] = 1.0f; o[3 * npix] = -1.0f; } else { o[npix] = -1.0f; }
+        OCCL_STORE(o, 1.0f);
+        if (p.obs_planes == 4) { OCCL_STORE(o + npix, 1.0f); OCCL_STORE(o + 2 * npix, 1.0f); OCCL_STORE(o + 3 * npix, -1.0f); } else { OCCL_STORE(o + npix, -1.0f); }
         for (int ob = 0; ob < p.n_obj; ++ob) {
           if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
           if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
@@ -2528,7 +2536,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       for (int b = a + 1; b < OCCL_MAX_OBJ; ++b)
         if (b < p.n_obj) occl = occl + A[a] * A[b];
     }
-    p.occl[(size_t)env * npix + pix] = occl;
+    OCCL_STORE(p.occl + (size_t)env * npix + pix, occl);
     acc_loss += (double)occl * (double)occl;
     acc_obj += (double)objs * (double)objs;
     if (GRAD) {
@@ -2572,13 +2580,13 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       rgb = sh.x * texel + sh.y;
     }
     float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
-    o[0] = rgb;
+    OCCL_STORE(o, rgb);
     if (p.obs_planes == 4) {
-      o[npix] = rgb;
-      o[2 * npix] = rgb;
-      o[3 * npix] = depth;
+      OCCL_STORE(o + npix, rgb);
+      OCCL_STORE(o + 2 * npix, rgb);
+      OCCL_STORE(o + 3 * npix, depth);
     } else {
-      o[npix] = depth;
+      OCCL_STORE(o + npix, depth);
     }
     if (DBG && p.pix_to_face) p.pix_to_face[(size_t)env * npix + pix] = pf;
     if (DBG && p.bary) {

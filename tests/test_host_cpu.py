@@ -212,3 +212,34 @@ def test_status_bits_match_header():
     bits = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define OCCL_ST_(\w+) (\d+)u", hdr)}
     assert bits == {"ZCLIP": L.ST_ZCLIP, "KOVERFLOW": L.ST_KOVERFLOW, "HITCAP": L.ST_HITCAP, "OVFCAP": L.ST_OVFCAP,
                     "CLIPPED": L.ST_CLIPPED}
+
+
+def test_workspace_is_sized_per_chunk_not_per_batch():
+    """the BASELINE config-3 shape (8192 envs x 61 440 faces x 256^2) must fit: the per-face scratch
+    is sized for a chunk of envs (OcclConfig.ws_budget_mb), 78 GB if it were sized for N."""
+    import ctypes
+    from occlusionenv_b200 import _lib as L
+    lib = L.load()
+
+    def ws(n, S, V, F, starts, budget=0, grad=0):
+        c = L.OcclConfig()
+        c.image_size, c.n_obj, c.n_verts, c.n_faces = S, len(starts) - 1, V, F
+        for i in range(L.OCCL_MAX_OBJ + 1):
+            c.obj_face_start[i] = starts[min(i, len(starts) - 1)]
+        c.faces_per_pixel, c.cull_backfaces, c.blur_radius, c.sigma, c.ws_budget_mb = 100, 1, 9.2e-4, 1e-4, budget
+        return lib.occl_workspace_bytes(ctypes.byref(c), n, grad)
+
+    c3 = ws(8192, 256, 30726, 61440, [0, 20480, 40960, 61440])
+    assert 0 < c3 <= 30 * 2 ** 30, c3
+    assert ws(8192, 256, 30726, 61440, [0, 20480, 40960, 61440], grad=1) <= 30 * 2 ** 30
+    c2 = ws(4096, 128, 1300, 2476, [0, 2464, 2476])
+    assert 0 < c2 < 2 * 2 ** 30
+    assert ws(4096, 128, 1300, 2476, [0, 2464, 2476], budget=64) < c2 // 4  # a smaller budget, smaller chunks
+
+
+def test_peer_view_slices_by_rows():
+    from occlusionenv_b200.dist import PeerView
+    v = PeerView(0x1000, (8, 2, 4, 4))
+    s = v[2:5]
+    assert s.shape == (3, 2, 4, 4) and s.data_ptr() == 0x1000 + 2 * 2 * 4 * 4 * 4
+    assert v[6:].shape == (2, 2, 4, 4)

@@ -237,3 +237,53 @@ def test_pose_gradient_golden(oracle):
     np.testing.assert_allclose(grad, g["dloss_del_daz"][2], rtol=1e-9)
     gold = np.load(os.path.join(GOLD, "scene_box_128.npz"))
     np.testing.assert_allclose(loss, float(gold["loss2"]), rtol=1e-5)
+
+
+def test_oracle_switches_toggle_and_restore():
+    """The discretionary choices of the restatement sit behind switches (tools/pin_with_pytorch3d.py flips them one at a
+    time against the real library); the defaults are what the kernels implement and every switch is small on the
+    teapot scene."""
+    from oracle import oracle as O
+    from occlusionenv_b200.meshes import default_scene
+    sc = default_scene("teapot")
+    _, _, C, R, T = O.pose_step(np.zeros(2, np.float32), 0.2, 1.4, 4.0)
+    base = O.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 32, C, R, T)
+    assert O.get_options() == {"trig_fp32": 0, "proj_matrix": 0, "neighbor_topk": 0, "clip_lerp_ndc": 0,
+                               "specular_center_inverse": 0}
+    for name in ("trig_fp32", "proj_matrix", "neighbor_topk", "clip_lerp_ndc", "specular_center_inverse"):
+        O.set_option(name, 1)
+        try:
+            assert O.get_options()[name] == 1
+            _, _, C2, R2, T2 = O.pose_step(np.zeros(2, np.float32), 0.2, 1.4, 4.0)
+            out = O.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 32, C2, R2, T2)
+        finally:
+            O.set_option(name, 0)
+        assert np.abs(out.alphas - base.alphas).max() < 1e-4 and np.abs(out.obs[:3] - base.obs[:3]).max() < 1e-5
+    again = O.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, 32, C, R, T)
+    assert np.array_equal(again.alphas, base.alphas) and np.array_equal(again.pix_to_face, base.pix_to_face)
+    import pytest
+    with pytest.raises(ValueError):
+        O.set_option("no_such_choice", 1)
+
+
+def test_clip_aware_gradient_oracle_matches_finite_differences():
+    """oracle/dense_torch.py through faces cut at z_clip: autograd == central differences of the same float64 loss with
+    the fp32 oracle's discrete decisions frozen, and the forward loss agrees with the fp32 oracle."""
+    from oracle import oracle as O, dense_torch as D
+    from occlusionenv_b200.meshes import default_scene
+    sc = default_scene("teapot")
+    S, r, az, el = 32, 1.8, 1.5, 0.3
+    act = np.array([0.3, -0.4])
+    args = (float(O.PROJ_SCALE), float(O.BLUR_RADIUS), float(O.SIGMA))
+    _, loss, g, _ = D.reward_and_grad(sc, S, act, el, az, r, 0.0, 1.0, *args, freeze_hits=True)
+    _, _, C, R, T = O.pose_step(act.astype(np.float32), np.float32(el), np.float32(az), np.float32(r))
+    out = O.render_scene(sc.verts, sc.faces, sc.obj_face_start, sc.obj_vert_start, S, C, R, T)
+    assert out.zclip_straddle and loss > 1.0
+    np.testing.assert_allclose(loss, float(out.loss), rtol=2e-5)
+    h = 1e-6
+    for k in range(2):
+        e = np.zeros(2)
+        e[k] = h
+        lp = D.reward_and_grad(sc, S, act + e, el, az, r, 0.0, 1.0, *args, freeze_hits=True)[1]
+        lm = D.reward_and_grad(sc, S, act - e, el, az, r, 0.0, 1.0, *args, freeze_hits=True)[1]
+        np.testing.assert_allclose(g[k], -(lp - lm) / (2 * h), rtol=1e-4, atol=1e-6)
