@@ -69,7 +69,7 @@ typedef struct OcclConfig {
   int32_t debug_exact;                      /* 1: evaluate every (pixel, face) pair with the reference's exact
                                                operation sequence (no guarded fast path); for parity tests */
   int32_t ws_budget_mb;                     /* cap, in MiB, of the rasteriser's per-face scratch inside the workspace
-                                               (0 = 2048): the batch is rasterised in chunks of as many envs as fit,
+                                               (0 = 8192): the batch is rasterised in chunks of as many envs as fit,
                                                so the workspace does not grow as N x F (occl_workspace_bytes) */
   int32_t obs_planes;                       /* 0 / 4: obs is (N,4,S,S) R, G, B, depth -- the reference's layout
                                                (environment.py:376-378); 2: (N,2,S,S) grey, depth -- the same

@@ -35,7 +35,7 @@ class RasterConfig:
     tile_h: int = 0
     debug_exact: bool = False                    # every pair through the reference-order arithmetic (tests)
     obs_planes: int = 4                          # 4: (N,4,S,S) RGB + depth (reference); 2: grey + depth (compact transport)
-    ws_budget_mb: int = 0                        # cap of the rasteriser's per-face scratch in MiB (0 = 2048): envs are
+    ws_budget_mb: int = 0                        # cap of the rasteriser's per-face scratch in MiB (0 = 8192): envs are
                                                  # rasterised in chunks that fit it, see occl_b200.h
 
     @property

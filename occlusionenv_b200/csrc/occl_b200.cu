@@ -76,6 +76,7 @@
 #ifndef FACES_PER_PASS
 #define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
 #endif
+#define OCCL_WS_BUDGET_MB 8192 // default cap of the per-face scratch (OcclConfig.ws_budget_mb = 0)
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
 #ifndef ROUND_FACES_FWD
 #define ROUND_FACES_FWD 256   // faces per round of the tile rasteriser's main phase (one per thread)
@@ -124,6 +125,15 @@ struct Partial {
   int ncov[OCCL_MAX_OBJ];
   int nvis[OCCL_MAX_OBJ];
 };
+
+// An opaque copy of a shared-memory base address.  ptxas, at a tight register cap, rebuilds every shared-window base from
+// SR_CgaCtaId where it is used (S2R + MOV + IADD + LEA, inside the hottest loops); an empty asm makes the value
+// unknown to it -- it then lives in a (uniform) register -- and the assume keeps LDS / STS / ATOMS instead of generic accesses.
+#define OCCL_OPAQUE_SHARED(ptr)                 \
+  do {                                          \
+    asm volatile("" : "+l"(ptr));               \
+    __builtin_assume(__isShared(ptr));          \
+  } while (0)
 
 __device__ __forceinline__ float pix_to_ndc(int i, int S) {
   // PixToNonSquareNdc for a square image: -1 + (2 i + 1) / S           
@@ -875,8 +885,16 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CTAS) face_setup_kernel(c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* tab = (float*)smem_raw;  // [S] pixel-centre table
   __shared__ int s_base, s_cut;
-  __shared__ uint32_t s_tmask[TILE_MASK_WORDS];
-  __shared__ int s_tcnt[BIN ? 32 * TILE_MASK_WORDS : 1];  // faces binned per tile (images of up to 256 tiles)
+  __shared__ uint32_t s_tmask_[TILE_MASK_WORDS];
+  __shared__ int s_tcnt_[BIN ? 32 * TILE_MASK_WORDS : 1];  // faces binned per tile (images of up to 256 tiles)
+  __shared__ int s_wl_[SETUP_WARPS][64];
+  uint32_t* s_tmask = s_tmask_;
+  int* s_tcnt = s_tcnt_;
+  int (*s_wl)[64] = s_wl_;
+  OCCL_OPAQUE_SHARED(tab);
+  OCCL_OPAQUE_SHARED(s_tmask);
+  OCCL_OPAQUE_SHARED(s_tcnt);
+  OCCL_OPAQUE_SHARED(s_wl);
   const int env = blockIdx.x;
   if (p.env_mask && !p.env_mask[env]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -896,7 +914,6 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CTAS) face_setup_kernel(c
   // dense over the queue, so that its lanes are busy whatever the cull rate.  List slots are reserved with one atomic
   // per pass: the list is in mesh order up to the interleaving of concurrently finishing warps (nothing depends on
   // its order).
-  __shared__ int s_wl[SETUP_WARPS][64];
   __shared__ int s_next;  // next 64-face chunk (the warps take chunks dynamically: the cull rate varies along the mesh)
   if (tid == 0) s_next = 0;
   __syncthreads();
@@ -1473,8 +1490,7 @@ __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(0xff
 // is recomputed here so that nothing extra stays live across the caller's main phase.
 template <bool GRAD, int TW, int TH, bool CLIPF, bool REC>
 __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const int env, const int tile, const int n_tidx,
-                                                  const RecCtx rc) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                  const RecCtx rc, unsigned char* smem_raw /* the caller's opaque base */) {
   const int tile_w = TW ? TW : p.tile_w, tile_h = TH ? TH : p.tile_h;
   const int tpx = tile_w * tile_h;
   const int tx0 = (tile % p.tiles_x) * tile_w, ty0 = (tile / p.tiles_x) * tile_h;
@@ -2093,8 +2109,13 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   __shared__ double s_red[OCCL_WARPS][4];
   __shared__ int s_redi[OCCL_WARPS][2 * OCCL_MAX_OBJ];
 
-  TileSmem sm = tile_smem_layout(smem_raw, tile_w, tile_h, p.n_obj);
-  sm.defer_n = &s_wdef_n[warp];
+  // opaque bases: three to four rebuilt addresses per trip of the pair loop otherwise
+  unsigned char* smem_base = smem_raw;
+  OCCL_OPAQUE_SHARED(smem_base);
+  int* wdef_base = s_wdef_n;
+  OCCL_OPAQUE_SHARED(wdef_base);
+  TileSmem sm = tile_smem_layout(smem_base, tile_w, tile_h, p.n_obj);
+  sm.defer_n = wdef_base + warp;
 
   // ---- tiles no live face touches: background only ---------------------------------------------
   if (n_tiles <= 32 * TILE_MASK_WORDS &&
@@ -2309,7 +2330,6 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
                   "recording queues must fit behind the round buffers");
     unsigned* rq = (unsigned*)(rb.pref + R + 1) + warp * (2 * RQ_CAP);
     sm.defer = sm.defer + warp * WDEFER_CAP;
-    sm.defer_n = &s_wdef_n[warp];
     const int n_src = binned ? n_bin : n_live;
     for (int base = 0; base < n_src; base += R) {
       // (a) one candidate per thread
@@ -2463,7 +2483,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
     const int n_t = s_tidx_n;
     const bool use_t = n_t <= p.tidx_cap;
     const int ctx0 = (tile % p.tiles_x) * tile_w, cty0 = (tile / p.tiles_x) * tile_h;
-    const TileSmem csm = tile_smem_layout(smem_raw, tile_w, tile_h, p.n_obj);
+    const TileSmem csm = tile_smem_layout(smem_base, tile_w, tile_h, p.n_obj);
     clip_phase(p.geo + (size_t)env * p.F * 4, p.rng + (size_t)env * p.F,
                p.tile_idx + ((size_t)env * n_tiles + tile) * p.tidx_cap, use_t ? n_t : p.n_live[env], use_t, ctx0, cty0,
                ctx0 + tile_w - 1, cty0 + tile_h - 1, csm.soft, csm.hard, csm.ndc_x, csm.ndc_y, tile_w, tile_w * tile_h, p.z_clip,
@@ -2472,7 +2492,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
   }
 
   // ---- pixels with more than K hits: keep the K nearest by (pz_clipped, face index) -------------
-  koverflow_resolve<GRAD, TW, TH, CLIPF, REC>(p, env, tile, s_tidx_n, rc);
+  koverflow_resolve<GRAD, TW, TH, CLIPF, REC>(p, env, tile, s_tidx_n, rc, smem_base);
   if (REC) {
     __syncthreads();
     if (tid == 0 && s_slab >= 0) atomicAnd(p.rec_table + s_slab / REC_CTAS_PER_SM, ~(1u << (s_slab % REC_CTAS_PER_SM)));
@@ -2919,8 +2939,10 @@ extern "C" int occl_config_resolve(OcclConfig* c, int with_grad) {
 // rasteriser (live-face records, pixel ranges, lighting, tile index lists: ~90 B per face plus 4 B per tile-list slot,
 // of which only the live / touched part is ever written) is sized for a CHUNK of envs and reused chunk after chunk on
 // the stream (face_setup -> raster -> raster_clip per chunk).  The chunk is the largest env count whose scratch fits
-// ws_budget_mb (default 2 GiB): 4096 envs x 2 476 faces (config 2) is one chunk, 8192 envs x 61 440 faces x 256^2
-// (config 3; 78 GB if sized for N) runs in chunks of ~220 envs.
+// ws_budget_mb (default 8 GiB): 4096 envs x 2 476 faces (config 2) is one chunk of 1.6 GB, 8192 envs x 61 440 faces x
+// 256^2 (config 3; 78 GB if sized for N) runs in chunks of ~430 envs.  Measured at config 3 (env-steps/s against the
+// budget): 1 GiB 21.9 k, 2 GiB 24.3 k, 4 GiB 26.4 k, 8 GiB 27.5 k, 12 GiB 27.8 k -- the setup kernel is one CTA per env,
+// so a chunk should hold several hundred envs to fill the GPU next to the other lane's raster launch.
 static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   const int tx = (c->image_size + c->tile_w - 1) / c->tile_w;
   const int ty = (c->image_size + c->tile_h - 1) / c->tile_h;
@@ -2928,7 +2950,7 @@ static int ws_layout(const OcclConfig* c, int n, int with_grad, WsLayout* L) {
   L->tidx_cap = c->n_faces < 8192 ? c->n_faces : 8192;
   const size_t per_env = (size_t)c->n_faces * (sizeof(uint4) * 5 + sizeof(float2)) + sizeof(int) * (size_t)L->n_tiles * (L->tidx_cap + 1) +
                          sizeof(int) + sizeof(uint32_t) * TILE_MASK_WORDS;
-  const size_t budget = (size_t)(c->ws_budget_mb > 0 ? c->ws_budget_mb : 2048) << 20;
+  const size_t budget = (size_t)(c->ws_budget_mb > 0 ? c->ws_budget_mb : OCCL_WS_BUDGET_MB) << 20;
   size_t chunk = budget / per_env;
   L->sets = 1;
   if (chunk < (size_t)n) {
