@@ -60,21 +60,13 @@
 #ifndef SETUP_CTAS
 #define SETUP_CTAS 4          // resident CTAs per SM the setup kernel is compiled for (64 registers, no spills: 32 warps hide its gather latency; 3 measured 1 % slower on C2)
 #endif
-#define WBUF_RECS 48          // face records staged per warp (up to BATCH_MIN - 1 pending + 32 new; the K-overflow hit buffer aliases it)
+#define WBUF_RECS 48          // 16-word records per warp of the tile's scratch region (24 KB per CTA): the round buffers of the main
+                              // phase, the difference image of the evaluate-once pre-pass and the K-overflow hit buffers alias it
 #ifndef OCCL_CTAS_FWD
 #define OCCL_CTAS_FWD 4       // resident CTAs per SM the forward kernel is compiled for (64 registers)
 #endif
 #ifndef OCCL_CTAS_GRAD
 #define OCCL_CTAS_GRAD 3      // ... and the differentiable kernel (80 registers)
-#endif
-#ifndef OCCL_RFP_INLINE
-#define OCCL_RFP_INLINE __forceinline__
-#endif
-#ifndef BATCH_MIN
-#define BATCH_MIN 8           // a warp rasterises its staged faces once this many are pending (8..16 measured equal)
-#endif
-#ifndef FACES_PER_PASS
-#define FACES_PER_PASS 4      // faces that share the 32 lanes of a warp in one pass of the pixel loop
 #endif
 #define OCCL_WS_BUDGET_MB 8192 // default cap of the per-face scratch (OcclConfig.ws_budget_mb = 0)
 #define WDEFER_CAP 128        // per-warp queue of inside hits awaiting their exact depth
@@ -82,16 +74,13 @@
 #define ROUND_FACES_FWD 256   // faces per round of the tile rasteriser's main phase (one per thread)
 #endif
 #define ROUND_FACES_GRAD 128  // ... of the differentiable kernel (its records also carry 48 B of vertex tangents)
-#ifndef BIG_FACE_PX
-#define BIG_FACE_PX 256       // faces covering more tile pixels than this are rasterised by the whole CTA (64..256 measured equal, 512 3 % slower)
-#endif
-#define BIG_CAP 16            // such faces per tile held in shared memory (more: the finding warp does them)
+#define BIG_CAP 16            // 16-word records of the small scratch region behind the depth queues (round tables of the K-overflow paths)
 #define CAND_CAP (256 * OCCL_WARPS)  /* 2048 */         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per round of the one-pixel fallback
 #define HITBUF_CAP (272 * OCCL_WARPS)  /* 2176 */       // hits (12 B each) of one selection round: aliases the face list + depth queue
 #define WQ_CAP 64             // (slot, face) pairs queued per warp for the dense evaluation of a round
-#define RSLOT_CAP 128         // (pixel, object) slots per selection round (table aliases the big-face records)
+#define RSLOT_CAP 128         // (pixel, object) slots per selection round (table lives in the small scratch region)
 // "Evaluate every hit once" (compile-time tiles of at most REC_MAX_TPX pixels: the dense-mesh and many-object tiles):
 // before the main phase the tile counts, per (pixel, object) slot, the faces whose blur box holds the pixel (an upper
 // bound U of its hits: a 2-D difference image + prefix sums); slots with U > K get a segment of U entries in the CTA's
@@ -1146,7 +1135,7 @@ struct TileSmem {
   float* ndc_y;              // [tile_h]
   uint32_t* list;            // [warps][WBUF_RECS][REC_WORDS]  (aliased by the top-K selection buffers)
   uint32_t* defer;           // [warps][WDEFER_CAP] inside hits awaiting their exact depth
-  uint32_t* big;             // [BIG_CAP][REC_WORDS] faces set aside for CTA-wide rasterisation
+  uint32_t* big;             // [BIG_CAP][REC_WORDS] small scratch region (slot / list tables of the K-overflow paths)
   int* defer_n;
 };
 
@@ -1520,9 +1509,9 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
     static_assert((size_t)HITBUF_CAP * 12 + 4 * OCCL_WARPS * WQ_CAP <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "hit buffer + pair queues must fit the face list");
     __shared__ int s_rn, s_todo, s_huge, s_rb[4], s_wsum[OCCL_WARPS];
     __shared__ unsigned s_robj;
-    int* s_rslot = (int*)sm.big;                                        // [RSLOT_CAP]  (big faces are done)
+    int* s_rslot = (int*)sm.big;                                        // [RSLOT_CAP]
     unsigned short* s_roff = (unsigned short*)(s_rslot + RSLOT_CAP);    // [RSLOT_CAP]
-    static_assert(RSLOT_CAP * 6 <= 4 * BIG_CAP * REC_WORDS, "round table must fit the big-face records");
+    static_assert(RSLOT_CAP * 6 <= 4 * BIG_CAP * REC_WORDS, "round table must fit the small scratch region");
     const int n_slots = tpx * p.n_obj;
     const int per = (n_slots + OCCL_THREADS - 1) / OCCL_THREADS;
     const int s_begin = min(tid * per, n_slots), s_end = min(s_begin + per, n_slots);
