@@ -794,12 +794,13 @@ __device__ __noinline__ void clip_hit_tangent(const RasterParams& p, const SubTr
   *g1 += kk * (gx * (wa * da.z + wb * db.z) + gy * (wa * da.w + wb * db.w));
 }
 
+__device__ __forceinline__ float soft_term(float signed_dist, float inv_sigma_log2e);
 // K-overflow round: hits of one cut face on the slots of the round (one lane; rare)
 __device__ __noinline__ void clip_round_hits(const uint4* __restrict__ rec, const uint4 rg, const int* s_rslot, const int rn,
                                              unsigned long long* soft_all, unsigned long long* hkey, float* hq,
                                              const float* ndc_x, const float* ndc_y, const int tx0, const int ty0,
                                              const int tile_w, const int tpx, const float z_clip, const int cull,
-                                             const float blur, const float bbox_r, const float sigma) {
+                                             const float blur, const float bbox_r, const float inv_sigma_log2e) {
   const int fx0 = (int)(rg.x & 0xffffu) - tx0, fx1 = (int)(rg.x >> 16) - tx0;
   const int fy0 = (int)(rg.y & 0xffffu) - ty0, fy1 = (int)(rg.y >> 16) - ty0;
   const int fobj = (int)(rg.w >> 30);
@@ -815,7 +816,7 @@ __device__ __noinline__ void clip_round_hits(const uint4* __restrict__ rec, cons
     const unsigned pos = atomicAdd((unsigned*)(soft_all + slot), 1u);
     if (pos < HITBUF_CAP) {
       hkey[pos] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)fidx;
-      hq[pos] = 1.0f - soft_prob(inside ? -dist : dist, sigma);
+      hq[pos] = soft_term(inside ? -dist : dist, inv_sigma_log2e);
     }
   }
 }
@@ -1106,6 +1107,16 @@ __device__ __forceinline__ float soft_product(unsigned long long w) {
   if (hi & SOFT_RESOLVED) return __uint_as_float(lo);
   if ((hi >> SOFT_STRONG_SHIFT) >= SOFT_STRONG_NEEDED) return 0.0f;
   return ex2_approx(-((float)lo * (1.0f / (float)(1u << SOFT_FRAC))));
+}
+// The K-overflow paths sum the terms of the hits they keep as 64-bit integers (32 fractional bits: these paths are cold,
+// and K hits of a far, tiny object can share one distance, so that 22-bit rounding errors would add up coherently):
+// alpha then depends on the SET of kept hits only, not on the order in which the hits arrived -- run-to-run
+// deterministic, like the main phase.
+__device__ __forceinline__ unsigned long long soft_term_fx(float term) {
+  return __float2ull_rn(term * 4294967296.0f);
+}
+__device__ __forceinline__ float soft_product_fx(unsigned long long fx) {
+  return ex2_approx(-((float)fx * (1.0f / 4294967296.0f)));
 }
 // strong-hit shortcut of the top-K rule: whatever K hits are the nearest, at most (count - strong) of them are weak
 __device__ __forceinline__ bool soft_strong_shortcut(unsigned hi, int K) {
@@ -1498,10 +1509,10 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
   // (pixel, object) slots -- in slot order, as many as their exactly known hit counts fit HITBUF_CAP -- and
   //  1. marks them (bit 29; the product word becomes the write cursor of the slot's segment),
   //  2. pairs every marked slot with the faces of the tile whose blur box holds its pixel (per-warp queues),
-  //     re-evaluates the pairs 32 at a time with the reference-order routine and appends (key, factor) of
+  //     re-evaluates the pairs 32 at a time with the reference-order routine and appends (key, term) of
   //     every hit to the slot's segment,
   //  3. one warp per slot finds the K-th smallest key by bisection over the key bits (early exit once the
-  //     K smallest are separated) and multiplies the factors below it.
+  //     K smallest are separated) and sums the (fixed-point) terms below it: product = 2^-sum.
   // Slots with more hits than a whole round holds are left to the one-pixel path below.
   {
     unsigned long long* hkey = (unsigned long long*)sm.list;  // [HITBUF_CAP]
@@ -1564,7 +1575,8 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             const int obj = slot / tpx, pix = slot - obj * tpx;
             const int ly = pix / tile_w, lx = pix - ly * tile_w;
             const int want = p.K - 1;           // 0-based rank of the last key kept (nn > K here)
-            float lsum = 0.f, g0 = 0.f, g1 = 0.f;
+            unsigned long long lsum = 0ull;
+            float g0 = 0.f, g1 = 0.f;
             constexpr int KR = 8;               // keys per lane held in registers: slots of up to 256 hits
             if (nn <= 32 * KR) {
               // the slot's keys are read ONCE; the ~12 counting passes of the bisection run on registers
@@ -1604,7 +1616,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
               for (int t = 0; t < KR; ++t) {
                 const int i = lane + 32 * t;
                 if (i < nn && kr[t] < bound) {
-                  lsum += terms[i];
+                  lsum += soft_term_fx(terms[i]);
                   if (GRAD) hit_tangent(p, env, (int)(kr[t] & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
                 }
               }
@@ -1646,7 +1658,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
               for (int i = lane; i < nn; i += 32) {
                 const unsigned long long key = keys[i];
                 if (!(key < bound)) continue;
-                lsum += terms[i];
+                lsum += soft_term_fx(terms[i]);
                 if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
               }
             }
@@ -1657,7 +1669,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             }
             if (lane == 0) {
               sm.soft[slot] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32) |
-                              (unsigned long long)__float_as_uint(ex2_approx(-lsum));
+                              (unsigned long long)__float_as_uint(soft_product_fx(lsum));
               if (GRAD) sm.gacc[slot] = pack2f(g0, g1);
             }
             __syncwarp();
@@ -1759,7 +1771,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
                 const unsigned pos = atomicAdd((unsigned*)(sm.soft + slot), 1u);  // low word = cursor
                 if (pos < HITBUF_CAP) {
                   hkey[pos] = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
-                  hq[pos] = 1.0f - soft_prob(r.inside ? -r.dist : r.dist, p.sigma);
+                  hq[pos] = soft_term(r.inside ? -r.dist : r.dist, p.inv_sigma_log2e);
                 }
               }
             }
@@ -1803,13 +1815,13 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
             if ((rg.z & RNG_CLIP) && ((robj >> (rg.w >> 30)) & 1u) &&
                 !(bx1 < (int)(rg.x & 0xffffu) || bx0 > (int)(rg.x >> 16) || by1 < (int)(rg.y & 0xffffu) || by0 > (int)(rg.y >> 16)))
               clip_round_hits(geo + (size_t)k * 4, rg, s_rslot, rn, sm.soft, hkey, hq, sm.ndc_x, sm.ndc_y, tx0, ty0, tile_w, tpx,
-                              p.z_clip, p.cull, p.blur, p.bbox_r, p.sigma);
+                              p.z_clip, p.cull, p.blur, p.bbox_r, p.inv_sigma_log2e);
           }
         }
       }
       __syncthreads();
       if (tid == 0) { s_rn = 0; s_todo = 0; s_huge = 0; s_rb[0] = 1 << 30; s_rb[1] = 1 << 30; s_rb[2] = -1; s_rb[3] = -1; s_robj = 0u; }
-      // 3. one warp per slot: K-th smallest key, product of the factors up to it
+      // 3. one warp per slot: K-th smallest key, sum of the terms up to it
       for (int r = warp; r < rn; r += OCCL_WARPS) {
         const int slot = s_rslot[r];
         const int off = (int)s_roff[r];
@@ -1846,22 +1858,24 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
           }
           if (!found) bound = prefix + 1ull;
         }
-        float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+        unsigned long long ls = 0ull;
+        float g0 = 0.f, g1 = 0.f;
         const int obj = slot / tpx, pix = slot - obj * tpx;
         const int ly = pix / tile_w, lx = pix - ly * tile_w;
         for (int i = lane; i < nn; i += 32) {
           const unsigned long long key = keys[i];
           if (!(key < bound)) continue;
-          pr = pr * hq[off + i];
+          ls += soft_term_fx(hq[off + i]);
           if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), sm.ndc_x[lx], sm.ndc_y[ly], &g0, &g1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+          ls += __shfl_down_sync(0xffffffffu, ls, o);
           if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
         }
         if (lane == 0) {
-          sm.soft[slot] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32) | (unsigned long long)__float_as_uint(pr);
+          sm.soft[slot] = ((unsigned long long)((hi & ~SOFT_ROUND) | SOFT_RESOLVED) << 32) |
+                          (unsigned long long)__float_as_uint(soft_product_fx(ls));
           if (GRAD) sm.gacc[slot] = pack2f(g0, g1);
         }
       }
@@ -1916,7 +1930,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
     //  A. the faces of this tile whose blur box holds the pixel are compacted into a candidate list,
     //  B. the candidates are evaluated densely (every thread has work) -> sort key (pz_clipped, face) and factor,
     //  C. the K-th smallest key is found (rank counting for short lists, 8-bit radix select otherwise),
-    //  D. the factors at or below that key are multiplied (the differentiable kernel re-evaluates those hits
+    //  D. the terms at or below that key are summed in fixed point (the differentiable kernel re-evaluates those hits
     //     for their tangent terms).
     for (int oi = 0; oi < n_ovf; ++oi) {
       const int slot = s_ovf[oi];
@@ -1928,7 +1942,7 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       const float px = sm.ndc_x[lx], py = sm.ndc_y[ly];
       static_assert((size_t)CAND_CAP * 12 <= (size_t)4 * OCCL_WARPS * (WBUF_RECS * REC_WORDS + WDEFER_CAP), "candidate buffers must fit the selection buffer");
       unsigned long long* ckey = (unsigned long long*)sm.list;  // [CAND_CAP]
-      float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its factor
+      float* cq = (float*)(ckey + CAND_CAP);                    // [CAND_CAP] candidate index, then its term -log2(1 - prob)
       __shared__ unsigned long long s_tau;
       __shared__ int s_hist[256];
       __shared__ int s_sel[2];
@@ -1982,10 +1996,10 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
           if (hit) pz = pz_clipped(g, r.b0, r.b1, r.b2);
         }
         unsigned long long key = ~0ull;
-        float q = 1.0f;
+        float q = 0.0f;  // the hit's term -log2(1 - prob)
         if (hit) {
           key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned long long)(q2.z & REC_FIDX_MASK);
-          q = 1.0f - soft_prob(inside ? -dist : dist, p.sigma);
+          q = soft_term(inside ? -dist : dist, p.inv_sigma_log2e);
           ++my_hits;
         }
         ckey[i] = key;
@@ -2043,23 +2057,26 @@ __device__ __forceinline__ void koverflow_resolve(const RasterParams p, const in
       }
       const unsigned long long tau = s_tau;
       // D
-      float pr = 1.0f, g0 = 0.f, g1 = 0.f;
+      unsigned long long ls = 0ull;
+      float g0 = 0.f, g1 = 0.f;
       for (int i = tid; i < nc; i += OCCL_THREADS) {
         const unsigned long long key = ckey[i];
         if (key > tau) continue;
-        pr = pr * cq[i];
+        ls += soft_term_fx(cq[i]);
         if (GRAD) hit_tangent(p, env, (int)(key & 0xffffffffull), px, py, &g0, &g1);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        pr = pr * __shfl_down_sync(0xffffffffu, pr, o);
+        ls += __shfl_down_sync(0xffffffffu, ls, o);
         if (GRAD) { g0 += __shfl_down_sync(0xffffffffu, g0, o); g1 += __shfl_down_sync(0xffffffffu, g1, o); }
       }
-      if (lane == 0) { s_red[warp][0] = (double)pr; s_red[warp][1] = (double)g0; s_red[warp][2] = (double)g1; }
+      if (lane == 0) { s_red[warp][0] = (double)ls; s_red[warp][1] = (double)g0; s_red[warp][2] = (double)g1; }  // (ls < 2^53: exact)
       __syncthreads();
       if (tid == 0) {
-        float P = 1.0f, G0 = 0.f, G1 = 0.f;
-        for (int w = 0; w < OCCL_WARPS; ++w) { P = P * (float)s_red[w][0]; G0 += (float)s_red[w][1]; G1 += (float)s_red[w][2]; }
+        double L = 0.0;
+        float G0 = 0.f, G1 = 0.f;
+        for (int w = 0; w < OCCL_WARPS; ++w) { L += s_red[w][0]; G0 += (float)s_red[w][1]; G1 += (float)s_red[w][2]; }
+        const float P = soft_product_fx((unsigned long long)L);
         const unsigned long long old = sm.soft[slot];
         sm.soft[slot] = (old & 0xffffffff00000000ull) | ((unsigned long long)SOFT_RESOLVED << 32) | (unsigned long long)__float_as_uint(P);
         if (GRAD) sm.gacc[(size_t)obj * tpx + pix] = pack2f(G0, G1);
