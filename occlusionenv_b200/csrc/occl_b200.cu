@@ -514,8 +514,9 @@ __device__ __forceinline__ void ndc_range_to_pixels(const float* __restrict__ ta
 
 // Pixel-independent part of CheckPixelInsideFace: the culls and `area`, preceded by the part of
 // pytorch3d's clip_faces (renderer/mesh/clip.py) that needs no new geometry: a face whose three vertices are
-// all nearer than z_clip is removed; a face that straddles z_clip would be cut into one or two new triangles
-// there -- not implemented: *straddles is reported and the caller raises OCCL_ST_ZCLIP.
+// all nearer than z_clip is removed; a face that straddles z_clip is cut into one or two new triangles there:
+// *straddles is reported, the setup kernel lists the env (clip_list) and the clip-capable instantiation of the tile
+// rasteriser rebuilds the cut triangles where it needs them (clip_subtris).
 __device__ __forceinline__ bool face_geo(const float4 a, const float4 b, const float4 c, int cull, float z_clip,
                                          FaceGeo* gp, bool* straddles) {
   FaceGeo& g = *gp;
