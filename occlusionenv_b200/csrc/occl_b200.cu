@@ -2670,10 +2670,14 @@ __global__ void mask_list_kernel(const int m, const uint8_t* __restrict__ mask, 
 template <int TW, int TH, bool DBG>
 __global__ void __launch_bounds__(OCCL_THREADS, OCCL_CTAS_FWD) raster_list_kernel(const RasterParams p) {
   const int n_tiles = p.tiles_x * p.tiles_y;
-  const int n_items = __ldg(p.env_list) * n_tiles;
+  const int n_env = __ldg(p.env_list);
+  const int n_items = n_env * n_tiles;
+  // items in tile-major order: a CTA's items (stride gridDim.x) then sweep through the tiles.  Env-major order gave CTA b
+  // the SAME tile of every env whenever n_tiles divides the grid (592 = 37 x 16): ten centre tiles here, ten empty corners there.
   for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int env = __ldg(p.env_list + 1 + it / n_tiles);
-    if (!(*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED)) raster_tile<false, TW, TH, DBG, false>(p, env, it % n_tiles);
+    const int tile = it / n_env;
+    const int env = __ldg(p.env_list + 1 + (it - tile * n_env));
+    if (!(*(volatile const uint32_t*)(p.status + env) & OCCL_ST_CLIPPED)) raster_tile<false, TW, TH, DBG, false>(p, env, tile);
     __syncthreads();
   }
 }
@@ -2686,10 +2690,12 @@ __global__ void __launch_bounds__(OCCL_THREADS, OCCL_CTAS_FWD) raster_list_kerne
 template <bool GRAD>
 __global__ void __launch_bounds__(OCCL_THREADS) raster_clip_kernel(const RasterParams p) {
   const int n_tiles = p.tiles_x * p.tiles_y;
-  const int n_items = __ldg(p.clip_list) * n_tiles;
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int env = __ldg(p.clip_list + 1 + it / n_tiles);
-    raster_tile<GRAD, 0, 0, true, true>(p, env, it % n_tiles);
+  const int n_env = __ldg(p.clip_list);
+  const int n_items = n_env * n_tiles;
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {  // tile-major, as in raster_list_kernel
+    const int tile = it / n_env;
+    const int env = __ldg(p.clip_list + 1 + (it - tile * n_env));
+    raster_tile<GRAD, 0, 0, true, true>(p, env, tile);
     __syncthreads();
   }
 }
