@@ -454,7 +454,10 @@ def run_ours(args, rank, world, local_rank):
         # pose, project, face_setup, raster, raster_clip (cut faces; CTAs leave at once otherwise), finalize
         "gpu_launches": 6 * K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "raster_kernel", "kernel_ms": raster_ms,
+                     "traffic": traffic, "kernel": "raster_kernel (timed together with the face_setup_kernel and "
+                     "raster_clip_kernel launches of the same occl_raster call: 86.5 % / 11.4 % / 0.1 % of the step in the "
+                     "ncu launch list, profiles/r02_launches_summary.txt; traffic is raster_kernel's alone)",
+                     "kernel_ms": raster_ms,
                      "kernel_share_of_step": raster_ms / (ms_total / K),
                      "algorithmic_bytes_per_env_step": bpe, "peak_source": peak_src,
                      "note": "issue-slot bound, not HBM bound: see DESIGN.md section 5"},
