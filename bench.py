@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "envs_per_gpu": N, "image_size": S, "occluder": args.occluder,
-                   "faces": 2476 if args.occluder == "box" else 4928, "faces_per_pixel": 100, "tile": [32, 32],
+                   "faces": 2476 if args.occluder == "box" else 4928, "faces_per_pixel": 100, "tile": [int(eng.c.tile_w), int(eng.c.tile_h)],
                    "l2": "outputs (obs+occlusion map: %.0f MB/step/GPU) larger than L2; no flush needed" % (N * S * S * 20 / 1e6),
                    "auto_reset": "excluded (see e2e.auto_reset)", "status_or": status},
         "clocks": clocks,
