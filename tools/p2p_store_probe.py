@@ -34,3 +34,29 @@ for target in ((0, 1) if torch.cuda.device_count() > 1 else (0,)):
         torch.cuda.synchronize()
         assert rc == 0 and float(dst[12345]) == 1.0
         print(f"device 0 -> device {target}: {tag:48s} {5 * n * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9:7.1f} GB/s", flush=True)
+
+# incast: every other GPU stores into device 0 at the same time (the learner's situation in config 5)
+nd = torch.cuda.device_count()
+if nd > 2:
+    import time
+    from occlusionenv_b200 import _lib as L
+    lib2 = L.load()
+    dst = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    part = n // (nd - 1) // 4096 * 4096
+    for d in range(1, nd):
+        torch.cuda.set_device(d)
+        torch.zeros(1, device=f"cuda:{d}")
+        L.check(lib2.occl_enable_peer_access(0), "occl_enable_peer_access")
+    for vec, pitch, rows, tag in ((1, 128, 32, "128 B segments, 512 B pitch"), (4, 128, 32, "512 B segments")):
+        for rep in range(2):   # first pass warms up
+            for d in range(1, nd):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                for d in range(1, nd):
+                    torch.cuda.set_device(d)
+                    lib.probe_launch(dst.data_ptr() + (d - 1) * part * 4, part, vec, pitch, rows, 148 * 8, torch.cuda.current_stream(d).cuda_stream)
+            for d in range(1, nd):
+                torch.cuda.synchronize(d)
+            dt = time.perf_counter() - t0
+        print(f"incast {nd - 1} GPUs -> device 0: {tag:40s} {5 * (nd - 1) * part * 4 / dt / 1e9:7.1f} GB/s into device 0", flush=True)
