@@ -482,6 +482,8 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
                        (peer-mapped gather buffer); only reward + done (5 B/env) go through NCCL
       p2p_fused_gray   the same with the compact 2-plane observation (grey + depth: the reference's R = G = B)
       double_buffered_gray  the double-buffered NCCL transfer with the compact observation
+      p2p_fused[_gray]_incremental  the fused delivery storing only the tiles that changed (lossless: background tiles that
+                       were background in the learner's buffer already stay as they are)
       features         row N-1: the frozen encoder on the env ranks, 256 floats per env to the learner"""
     import torch
     from occlusionenv_b200.config import RasterConfig
@@ -496,7 +498,7 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
     out = {"envs_per_gpu": N, "envs_total": N * world, "image_size": S,
            "collective": "obs/reward/done of every rank -> learner rank 0 over NVLink"}
 
-    def leg(name, planes, transport, halves):
+    def leg(name, planes, transport, halves, incremental=False):
         cfg = RasterConfig(image_size=S, obs_planes=planes)
         H = N // halves
         engs = [OcclusionEngine(sc, H, cfg, device=dev) for _ in range(halves)]
@@ -504,6 +506,8 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
             e.reset(radius=4.0, azimuth=az[k * H:(k + 1) * H], elevation=el[k * H:(k + 1) * H])
         lgs = [LearnerGather(H, (planes, S, S), dev, dst=0, transport=transport) for _ in range(halves)]
         bufs = [lg.obs_send_buffer() for lg in lgs]
+        # incremental delivery: tiles that were background in the learner's buffer and still are do not travel again
+        states = [e.incremental_obs(b) for e, b in zip(engs, bufs)] if incremental else None
         main = torch.cuda.current_stream()
         if halves == 1:
             def step(i):
@@ -543,6 +547,20 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
         out[name] = {"value": world * N * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "obs_planes": planes,
                      "transport": transport, "bytes_to_learner_per_step": nbytes,
                      "learner_ingest_gbs": nbytes / (ms / K * 1e-3) / 1e9}
+        if incremental:
+            n_tiles = (S // 32) ** 2 if S % 32 == 0 and (S // 32) ** 2 <= 32 else None
+            if n_tiles:
+                st = states[0][:, 8].to(torch.int64) & 0xffffffff
+                kept = 1.0 - float(sum(((st >> b) & 1).sum() for b in range(n_tiles))) / (st.numel() * n_tiles)
+                t = torch.tensor([kept], device=dev)
+                if world > 1:
+                    h.dist.all_reduce(t)
+                kept = float(t.item()) / world
+                out[name].update({"incremental": True, "tiles_stored_fraction_last_step": kept,
+                                  "bytes_to_learner_per_step": int(nbytes * kept),
+                                  "learner_ingest_gbs": nbytes * kept / (ms / K * 1e-3) / 1e9,
+                                  "note": "lossless: tiles that were background in the learner's buffer and still are "
+                                          "are not stored again (OcclOutputs.obs_tile_state)"})
         del engs, lgs, bufs
         torch.cuda.empty_cache()
 
@@ -592,9 +610,10 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
     leg("serial", 4, "nccl", 1)
     leg("double_buffered", 4, "nccl", 2)
     leg("double_buffered_gray", 2, "nccl", 2)
-    for name, planes in (("p2p_fused", 4), ("p2p_fused_gray", 2)):
+    for name, planes, inc in (("p2p_fused", 4, False), ("p2p_fused_gray", 2, False), ("p2p_fused_incremental", 4, True),
+                              ("p2p_fused_gray_incremental", 2, True)):
         try:
-            leg(name, planes, "p2p", 1)
+            leg(name, planes, "p2p", 1, incremental=inc)
         except Exception as ex:  # CUDA IPC unavailable (e.g. a container without peer access): reported, not hidden
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     try:

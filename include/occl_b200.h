@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define OCCL_ABI_VERSION 2
+#define OCCL_ABI_VERSION 3
 #define OCCL_MAX_OBJ 4
 #define OCCL_CAM_STRIDE 48 /* floats per env in the camera block, see occl_pose_* */
 
@@ -124,7 +124,16 @@ typedef struct OcclOutputs {
   uint32_t* status_or;   /* [opt] (1,) running OR of every status word written through this struct:
                             ORed into, never cleared, by occl_finalize / occl_step / occl_reset / occl_render
                             (the caller zeroes it when it has looked) -- one word to check instead of (N,) */
+  uint32_t* obs_tile_state; /* [opt] (N, OCCL_TILE_STATE_WORDS) INCREMENTAL delivery of `obs`: the state of the
+                            destination `obs` points to, owned by the caller next to that destination and filled with
+                            0xFF bytes before the first transition into it (and whenever somebody else wrote there).
+                            Words 0..7 of an env: bit t = tile t held a face at the last render; the library updates them.
+                            A tile that was background at the last render and is background now is NOT stored again
+                            (its pixels already are (1,1,1,-1)): the destination ends bit-identical to a full write while a
+                            peer destination receives only the tiles that changed.  Ignored (full writes) for images of
+                            more than 256 tiles.  NULL = every pixel is written.                                        */
 } OcclOutputs;
+#define OCCL_TILE_STATE_WORDS 16
 
 int occl_abi_version(void);
 

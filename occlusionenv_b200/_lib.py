@@ -6,7 +6,7 @@ import ctypes
 import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
-OCCL_ABI_VERSION = 2
+OCCL_ABI_VERSION = 3
 OCCL_MAX_OBJ = 4
 OCCL_CAM_STRIDE = 48
 
@@ -53,7 +53,10 @@ class OcclOutputs(Structure):
                 ("loss", c_void_p), ("position", c_void_p), ("n_covered", c_void_p),
                 ("n_visible", c_void_p), ("status", c_void_p), ("grad_action", c_void_p),
                 ("alphas", c_void_p), ("pix_to_face", c_void_p), ("bary", c_void_p), ("nhits", c_void_p),
-                ("status_or", c_void_p)]
+                ("status_or", c_void_p), ("obs_tile_state", c_void_p)]
+
+
+OCCL_TILE_STATE_WORDS = 16  # per env: 8 words "tile held a face at the last render" + 8 words of the current skip mask
 
 
 # every symbol include/occl_b200.h declares

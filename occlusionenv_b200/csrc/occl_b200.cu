@@ -77,6 +77,7 @@
 #define BIG_CAP 16            // 16-word records of the small scratch region behind the depth queues (round tables of the K-overflow paths)
 #define CAND_CAP (256 * OCCL_WARPS)  /* 2048 */         // candidate faces of ONE overflowing pixel (12 B each in the selection buffers)
 #define TILE_MASK_WORDS 8     // per-env bitmask of non-empty tiles (up to 256 tiles; more: mask unused)
+static_assert(OCCL_TILE_STATE_WORDS == 2 * TILE_MASK_WORDS, "OcclOutputs.obs_tile_state: last mask + skip mask per env");
 #define OVF_CAP 128           // overflowing (pixel, object) pairs handled per round of the one-pixel fallback
 #define HITBUF_CAP (272 * OCCL_WARPS)  /* 2176 */       // hits (12 B each) of one selection round: aliases the face list + depth queue
 #define WQ_CAP 64             // (slot, face) pairs queued per warp for the dense evaluation of a round
@@ -328,6 +329,7 @@ struct RasterParams {
   uint4* rng;    // [N][F]     pixel ranges: soft x, soft y, hard x, hard y  (lo | hi << 16); object id in bits 30..31 of .w
   int* n_live;   // [N]
   const uint32_t* tile_mask;  // [N][TILE_MASK_WORDS]
+  const uint32_t* obs_tile_state;  // [N][OCCL_TILE_STATE_WORDS] or null: words 8..15 = tiles whose obs need not be stored
   const float2* shade;        // [N][F]
   int* tile_idx;              // [N][n_tiles][tidx_cap] live-list indices of the faces that touch a tile
   int tidx_cap;
@@ -857,6 +859,7 @@ struct SetupParams {
   uint4* rng;
   int* n_live;
   uint32_t* tile_mask;  // [N][TILE_MASK_WORDS] bit t set: some live face's blur box overlaps tile t
+  uint32_t* obs_tile_state;  // [N][OCCL_TILE_STATE_WORDS] or null (OcclOutputs.obs_tile_state): incremental delivery of obs
   int* tile_idx;        // [N][n_tiles][tidx_cap] binning: live-list indices of the faces whose blur box overlaps a tile
   int* tile_cnt;        // [N][n_tiles] their number (may exceed tidx_cap: the raster kernel then scans the whole live list)
   int tidx_cap;
@@ -1028,7 +1031,17 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_CTAS) face_setup_kernel(c
   __syncthreads();
   if (tid == 0 && s_cut) p.clip_list[1 + atomicAdd(p.clip_list, 1)] = env;  // raster_clip_kernel works through this list
   if (tid == 0) p.n_live[env] = s_base;
-  if (tid < TILE_MASK_WORDS) p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = s_tmask[tid];
+  if (tid < TILE_MASK_WORDS) {
+    const uint32_t cur = s_tmask[tid];
+    p.tile_mask[(size_t)env * TILE_MASK_WORDS + tid] = cur;
+    if (p.obs_tile_state) {
+      // incremental delivery: a tile that was background in the destination and is background now keeps its pixels
+      uint32_t* st = p.obs_tile_state + (size_t)env * OCCL_TILE_STATE_WORDS;
+      const uint32_t prev = st[tid];
+      st[TILE_MASK_WORDS + tid] = ~prev & ~cur;
+      st[tid] = cur;
+    }
+  }
   if (BIN)
     for (int t = tid; t < p.n_tiles; t += SETUP_THREADS) p.tile_cnt[(size_t)env * p.n_tiles + t] = s_tcnt[t];
 }
@@ -2129,6 +2142,9 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       !((__ldg(p.tile_mask + (size_t)env * TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u)) {
     const size_t npix = (size_t)S * S;
     const bool debug_out = DBG && (p.alphas || p.nhits || p.pix_to_face || p.bary);
+    // incremental delivery (OcclOutputs.obs_tile_state): the destination already holds this tile's background
+    const bool keep_obs = p.obs_tile_state != nullptr &&
+        ((__ldg(p.obs_tile_state + (size_t)env * OCCL_TILE_STATE_WORDS + TILE_MASK_WORDS + (tile >> 5)) >> (tile & 31)) & 1u);
     if (!debug_out && (tile_w & 3) == 0 && (S & 3) == 0) {
       // 16-byte stores: four pixels of a row per thread and plane
       const int qw = tile_w >> 2;
@@ -2142,6 +2158,7 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
         if (xi >= S || yi >= S) continue;
         const size_t pix = (size_t)yi * S + xi;
         OCCL_STORE4(p.occl + (size_t)env * npix + pix, zero4);
+        if (keep_obs) continue;
         float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
         OCCL_STORE4(o, one4);
         if (p.obs_planes == 4) {
@@ -2160,9 +2177,11 @@ __device__ __forceinline__ void raster_tile(const RasterParams& p, const int env
       if (xi >= S || yi >= S) continue;
       const size_t pix = (size_t)yi * S + xi;
       OCCL_STORE(p.occl + (size_t)env * npix + pix, 0.f);
-      float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
-      OCCL_STORE(o, 1.0f);
-      if (p.obs_planes == 4) { OCCL_STORE(o + npix, 1.0f); OCCL_STORE(o + 2 * npix, 1.0f); OCCL_STORE(o + 3 * npix, -1.0f); } else { OCCL_STORE(o + npix, -1.0f); }
+      if (!keep_obs) {
+        float* o = p.obs + (size_t)env * p.obs_planes * npix + pix;
+        OCCL_STORE(o, 1.0f);
+        if (p.obs_planes == 4) { OCCL_STORE(o + npix, 1.0f); OCCL_STORE(o + 2 * npix, 1.0f); OCCL_STORE(o + 3 * npix, -1.0f); } else { OCCL_STORE(o + npix, -1.0f); }
+      }
       for (int ob = 0; ob < p.n_obj; ++ob) {
         if (DBG && p.alphas) p.alphas[((size_t)env * p.n_obj + ob) * npix + pix] = 0.f;
         if (DBG && p.nhits) p.nhits[((size_t)env * p.n_obj + ob) * npix + pix] = 0;
@@ -3144,6 +3163,8 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
   }
   p.obs = out.obs; p.obs_planes = c.obs_planes == 2 ? 2 : 4; p.occl = out.occl; p.alphas = out.alphas; p.pix_to_face = out.pix_to_face; p.bary = out.bary;
   p.nhits = out.nhits; p.status = out.status; p.env_mask = mask;
+  // incremental delivery needs the tile mask (images of at most 256 tiles)
+  p.obs_tile_state = L.n_tiles <= 32 * TILE_MASK_WORDS ? out.obs_tile_state : nullptr;
   const size_t smem = tile_smem_bytes(&c, grad);
   if ((long long)L.chunk * L.n_tiles > 0x7fffffffLL) return OCCL_E_INVALID;
   SetupParams sp;
@@ -3209,9 +3230,11 @@ static int raster_impl(const OcclConfig* cfg, int n, OcclScene sc, OcclWorkspace
     p.bary = p0.bary ? p0.bary + e * npix * 3 : nullptr;
     p.nhits = p0.nhits ? p0.nhits + e * c.n_obj * npix : nullptr;
     p.status = p0.status + e;
+    p.obs_tile_state = p0.obs_tile_state ? p0.obs_tile_state + e * OCCL_TILE_STATE_WORDS : nullptr;
     p.env_mask = p0.env_mask ? p0.env_mask + e : nullptr;
     sp.vproj = p.vproj; sp.faces = p.faces; sp.verts = p.verts; sp.cam = p.cam; sp.status = p.status;
     sp.env_mask = p.env_mask;
+    sp.obs_tile_state = (uint32_t*)p.obs_tile_state;
     const long long blocks = (long long)m * L.n_tiles;
     const unsigned clip_grid = (unsigned)(blocks < 2 * 148 ? blocks : 2 * 148);
     if (bin) face_setup_kernel<true><<<m, SETUP_THREADS, sizeof(float) * (size_t)c.image_size, lane>>>(sp);

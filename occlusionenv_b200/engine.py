@@ -117,6 +117,7 @@ class OcclusionEngine:
         else:
             self.alphas = self.pix_to_face = self.bary = self.nhits = None
         self._out_cache = {}
+        self._tile_state = {}  # destination pointer -> (N, 16) tile state of an incremental delivery (incremental_obs)
         nbytes = self.lib.occl_workspace_bytes(ctypes.byref(c), N, 1)
         if nbytes == 0:
             raise L.OcclError("occl_workspace_bytes returned 0 (invalid configuration)")
@@ -138,6 +139,8 @@ class OcclusionEngine:
             self._out_cache.pop(next(iter(self._out_cache)))
         o.obs = (self.obs if obs is None else obs).data_ptr()
         o.status_or = self.status_or.data_ptr()
+        st = self._tile_state.get(o.obs)
+        o.obs_tile_state = st.data_ptr() if st is not None else None
         if scratch:
             if getattr(self, "_scratch", None) is None:
                 self._scratch = dict(occl=torch.empty_like(self.occl), loss=torch.empty_like(self.loss),
@@ -162,6 +165,21 @@ class OcclusionEngine:
             o.bary = self.bary.data_ptr()
             o.nhits = self.nhits.data_ptr()
         return o
+
+    def incremental_obs(self, obs: Optional[torch.Tensor] = None, enable: bool = True) -> Optional[torch.Tensor]:
+        """Incremental delivery of the observation into ``obs`` (default: the engine's own buffer; typically a slice of the
+        learner's gather buffer in peer memory): a tile that was background at the last render into this destination and
+        is background now is not stored again (``OcclOutputs.obs_tile_state``).  The destination stays bit-identical to
+        a full write as long as nobody else writes into it -- call again to start over if somebody did.  Returns the
+        (N, 16) state tensor that travels with the destination."""
+        key = (self.obs if obs is None else obs).data_ptr()
+        self._out_cache.clear()
+        if not enable:
+            self._tile_state.pop(key, None)
+            return None
+        st = torch.full((self.n, L.OCCL_TILE_STATE_WORDS), -1, dtype=torch.int32, device=self.device)  # 0xFF bytes
+        self._tile_state[key] = st
+        return st
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -312,3 +312,64 @@ def test_config3_dense_batch_properties(cuda_lib):
     (gradf, _), _ = run(0, True)
     for n, x, y in zip(names, first, gradf):
         assert torch.equal(x, y), f"differentiable kernel's forward outputs differ: {n}"
+
+
+def test_incremental_observation_delivery_is_lossless(cuda_lib):
+    """OcclOutputs.obs_tile_state: tiles that were background at the last render into a destination and are background
+    now are not stored again.  After a reset, steps that move the objects across tiles, a masked reset and a
+    differentiable step the destination is bit-identical to the fully written one -- also for the two-plane layout, an
+    external destination tensor and a chunked workspace -- and tiles really are skipped (a poisoned skip survives)."""
+    from occlusionenv_b200.engine import OcclusionEngine
+    N, S = 96, 128
+    sc = default_scene("box")
+    g = torch.Generator().manual_seed(5)
+    az = (math.pi / 2 - 0.9) + 1.8 * torch.rand(N, generator=g)
+    el = -0.5 + torch.rand(N, generator=g)
+    acts = [torch.randn(N, 2, generator=g).cuda() for _ in range(6)]
+    mask = (torch.rand(N, generator=g) < 0.4).cuda()
+    for planes, budget in ((4, 0), (2, 0), (4, 8)):
+        cfg = RasterConfig(image_size=S, obs_planes=planes, ws_budget_mb=budget)
+        full = OcclusionEngine(sc, N, cfg)
+        inc = OcclusionEngine(sc, N, cfg)
+        dest = torch.full((N, planes, S, S), 7.0, device="cuda")     # an external destination with foreign content
+        state = inc.incremental_obs(dest)
+        assert state.shape == (N, 16)
+
+        def both(fn):
+            fn(full, None)
+            fn(inc, dest)
+            torch.cuda.synchronize()
+            assert torch.equal(full.obs, dest), (planes, budget)
+            for name in ("occl", "loss", "done", "n_covered", "n_visible"):
+                assert torch.equal(getattr(full, name), getattr(inc, name)), name
+
+        both(lambda e, d: e.reset(radius=4.0, azimuth=az, elevation=el, obs=d))
+        for k, a in enumerate(acts):
+            both(lambda e, d: e.step(a, with_grad=(k == 3), obs=d))
+            if k == 2:
+                both(lambda e, d: e.reset(radius=4.0, azimuth=0.0, elevation=0.0, mask=mask, obs=d))
+        # tiles are really skipped: poison the destination where the state says "background before and now"
+        skip = state[:, 8].clone()                                    # tiles 0..31 (a 128^2 image has 16)
+        assert int(skip.ne(0).sum()) > 0
+        e0 = int(torch.nonzero(skip)[0])
+        t0 = int(torch.nonzero(torch.tensor([(int(skip[e0]) >> b) & 1 for b in range(16)]))[0])
+        ty, tx = divmod(t0, S // 32)
+        inc.step(acts[0], obs=dest)
+        full.step(acts[0])
+        torch.cuda.synchronize()
+        assert torch.equal(full.obs, dest)
+        poisoned = bool((int(state[e0, 8]) >> t0) & 1)
+        if poisoned:
+            dest[e0, 0, ty * 32, tx * 32] = 123.0
+        inc.step(-acts[0], obs=dest)
+        full.step(-acts[0])
+        torch.cuda.synchronize()
+        if poisoned and ((int(state[e0, 8]) >> t0) & 1):
+            assert float(dest[e0, 0, ty * 32, tx * 32]) == 123.0   # background before and now: not rewritten
+        # ... and starting over restores a full write
+        inc.incremental_obs(dest)
+        dest.fill_(9.0)
+        inc.step(acts[1], obs=dest)
+        full.step(acts[1])
+        torch.cuda.synchronize()
+        assert torch.equal(full.obs, dest)
