@@ -606,20 +606,26 @@ def run_gather_legs(h, args, rank, world, dev, K, W):
                                       "(the reference's checkpoint is not in its tree), torch/cuDNN convolutions, "
                                       f"fp32 storage, allow_tf32={bool(torch.backends.cudnn.allow_tf32)}"}
 
-    step_only()
-    leg("serial", 4, "nccl", 1)
-    leg("double_buffered", 4, "nccl", 2)
-    leg("double_buffered_gray", 2, "nccl", 2)
+    only = set(x for x in args.gather_legs.split(",") if x)
+    want = lambda name: not only or name in only
+    if want("step_only"):
+        step_only()
+    for name, planes, halves in (("serial", 4, 1), ("double_buffered", 4, 2), ("double_buffered_gray", 2, 2)):
+        if want(name):
+            leg(name, planes, "nccl", halves)
     for name, planes, inc in (("p2p_fused", 4, False), ("p2p_fused_gray", 2, False), ("p2p_fused_incremental", 4, True),
                               ("p2p_fused_gray_incremental", 2, True)):
+        if not want(name):
+            continue
         try:
             leg(name, planes, "p2p", 1, incremental=inc)
         except Exception as ex:  # CUDA IPC unavailable (e.g. a container without peer access): reported, not hidden
             out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
-    try:
-        features_leg()
-    except Exception as ex:
-        out["features"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    if want("features"):
+        try:
+            features_leg()
+        except Exception as ex:
+            out["features"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     best = max((v["value"] for k, v in out.items() if isinstance(v, dict) and "value" in v and k != "step_only"), default=None)
     out["value"], out["unit"] = best, UNIT
     return out
@@ -637,6 +643,7 @@ def main():
     ap.add_argument("--grad", action="store_true", help="differentiable step (config 4)")
     ap.add_argument("--no-gather", action="store_true", help="world > 1: skip the learner-boundary legs (config 5)")
     ap.add_argument("--gather-envs", type=int, default=8192, help="envs per GPU of the config-5 legs")
+    ap.add_argument("--gather-legs", default="", help="comma-separated subset of the config-5 legs (default: all)")
     ap.add_argument("--no-configs", action="store_true", help="N = 1: skip config_results (config 4 and config 3)")
     ap.add_argument("--c3-envs", type=int, default=8192)
     ap.add_argument("--c3-steps", type=int, default=20)
