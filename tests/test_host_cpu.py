@@ -243,3 +243,19 @@ def test_peer_view_slices_by_rows():
     s = v[2:5]
     assert s.shape == (3, 2, 4, 4) and s.data_ptr() == 0x1000 + 2 * 2 * 4 * 4 * 4
     assert v[6:].shape == (2, 2, 4, 4)
+
+
+def test_struct_fields_match_header_in_order():
+    """The ctypes mirrors list the header's struct members in the header's order (a silent mismatch would shift every
+    pointer), and the tile-state width of the incremental delivery is the header's."""
+    from occlusionenv_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "occl_b200.h")).read()
+    for name, cls in (("OcclConfig", L.OcclConfig), ("OcclScene", L.OcclScene), ("OcclState", L.OcclState),
+                      ("OcclWorkspace", L.OcclWorkspace), ("OcclOutputs", L.OcclOutputs)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        members = [re.search(r"(\w+)\s*(\[[^\]]*\])?\s*$", part.strip()).group(1)
+                   for d in body.split(";") if d.strip() for part in d.split(",")]      # "int32_t tile_w, tile_h;"
+        assert members == [f[0] for f in cls._fields_], (name, members)
+    assert int(re.search(r"#define OCCL_TILE_STATE_WORDS (\d+)", hdr).group(1)) == L.OCCL_TILE_STATE_WORDS
+    assert int(re.search(r"#define OCCL_ABI_VERSION (\d+)", hdr).group(1)) == L.OCCL_ABI_VERSION
